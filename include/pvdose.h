@@ -1,0 +1,144 @@
+/* pvdose.h - C ABI of libpvdose.so: B200-native (sm_100a) kernel-convolution dose path.
+ *
+ * This is the drop-in boundary for ONE hot path of devhliu/PyVoxelDosimetry.  The reference has
+ * no FFI of its own (it is pure Python); each entry point below names the reference interface
+ * (file:line under /root/reference) whose arithmetic it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds to the reference.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types.
+ *  - All array pointers are DEVICE pointers owned by the caller unless the name starts with
+ *    `h_` (host).  Volumes are dense C-order [n0][n1][n2] float32 (the reference's NumPy
+ *    arr[x, y, z] layout, z contiguous: examples/kernel_convolution_example.py:17).
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued, not synchronised, unless
+ *    stated.
+ *  - Every function returns 0 on success or a negative PVD_ERR_* code; pvd_last_error()
+ *    returns a thread-local message.  No hidden device allocation: the caller provides the
+ *    workspace (pvd_plan_workspace_bytes / pvd_plan_set_workspace).
+ */
+#ifndef PVDOSE_H
+#define PVDOSE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVD_VERSION 100
+
+#define PVD_OK 0
+#define PVD_ERR_INVALID (-1)     /* bad argument */
+#define PVD_ERR_CUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
+#define PVD_ERR_STATE (-3)       /* workspace / kernel not set */
+#define PVD_ERR_NONFINITE (-4)   /* dose kernel contains NaN/Inf (the reference's own Y90 kernel does:
+                                    data/dose_kernels/y90_kernel.py:134-138) */
+#define PVD_ERR_UNSUPPORTED (-5) /* size outside what the engine handles */
+
+/* Boundary semantics of the convolution. */
+#define PVD_BOUNDARY_REFERENCE 0 /* circular over the activity grid, kernel anchored (cropped / zero padded) at
+                                    index (0,0,0): exactly np.fft.ifftn(fftn(a) * fftn(k, a.shape)).real,
+                                    core/kernel_convolution.py:71-74 */
+#define PVD_BOUNDARY_SAME 1      /* zero boundary, kernel centred at k//2 (generator convention,
+                                    data/dose_kernels/y90_kernel.py:34): == reference op on the zero padded
+                                    volume, cropped at the kernel centre */
+
+#define PVD_ALGO_AUTO 0
+#define PVD_ALGO_FFT 1    /* hand-written Stockham 3-D real FFT convolution */
+#define PVD_ALGO_DIRECT 2 /* direct tiled convolution, TMA-staged halo tiles (small kernels) */
+
+#define PVD_MAX_T 16 /* activity volumes fused into one execute call */
+
+typedef struct pvd_plan pvd_plan;
+
+typedef struct pvd_plan_info {
+    int n[3];      /* input extents */
+    int m[3];      /* transform extents */
+    int out_lo[3]; /* first output index per axis (in transform coordinates) */
+    int out_n[3];  /* output extents */
+    int k[3];      /* kernel extents */
+    int algo;      /* PVD_ALGO_FFT or PVD_ALGO_DIRECT (AUTO resolved) */
+    int passes;    /* kernel launches per execute */
+    size_t workspace_bytes;
+    double hbm_bytes_per_execute; /* bytes the implementation moves through HBM per execute (T=1, density) */
+} pvd_plan_info;
+
+int pvd_version(void);
+const char* pvd_last_error(void);
+
+/* Smallest transform length >= n the engine handles efficiently ({2,3,5,7}-smooth, few radix stages). */
+int pvd_good_fft_size(int n);
+
+/* ---- A1: KernelConvolutionCalculator.calculate_dose_rate (core/kernel_convolution.py:48-76) ----
+ * Plan for convolving [n0][n1][n2] activity volumes with a [k0][k1][k2] dose voxel kernel. */
+int pvd_plan_create(pvd_plan** out, const int n[3], const int k[3], int boundary, int algo);
+
+/* Expert form used by the z-slab decomposition (slab-plus-halo input, interior output):
+ * transform extents m[i] (0 = choose), outputs taken from transform indices
+ * [out_lo[i], out_lo[i] + out_n[i]).  The kernel is anchored at the origin of the circular
+ * domain of extents m, so out_lo = k//2 with m >= n + k - 1 - k//2 gives `same` semantics. */
+int pvd_plan_create_ex(pvd_plan** out, const int n[3], const int m[3], const int out_lo[3], const int out_n[3],
+                       const int k[3], int algo);
+
+int pvd_plan_get_info(const pvd_plan* plan, pvd_plan_info* info);
+int pvd_plan_workspace_bytes(const pvd_plan* plan, size_t* bytes);
+/* Workspace must be 256-byte aligned device memory of at least workspace_bytes; it holds the twiddle
+ * tables, the complex work buffer and the cached kernel spectrum. */
+int pvd_plan_set_workspace(pvd_plan* plan, void* workspace, size_t bytes, void* stream);
+
+/* Upload the dose voxel kernel (dense [k0][k1][k2] float32, device).  Validates finiteness
+ * (synchronises `stream` once) and builds the cached spectrum: the reference recomputes
+ * fftn(kernel) on every call (core/kernel_convolution.py:73). */
+int pvd_plan_set_kernel(pvd_plan* plan, const float* kernel, void* stream);
+
+/* dose = scale * conv( sum_t h_weights[t] * act[t], kernel ) [* rho_ref / max(rho, rho_min)]
+ *  - T = 1, h_weights = NULL           : A1 dose rate (core/kernel_convolution.py:71-74)
+ *  - T > 1, trapezoid weights          : A2 calculate_absorbed_dose (core/kernel_convolution.py:94-106)
+ *                                        evaluated as ONE convolution by linearity
+ *  - density != NULL                   : A9 voxel-wise density correction (the `tissue_densities`
+ *                                        argument the reference accepts and ignores, core/dose_calculator.py:90);
+ *                                        voxels with rho < rho_cut are zeroed (rho_cut <= 0 disables)
+ * h_act is a HOST array of T device pointers; h_weights a HOST array of T floats (NULL = all 1). */
+int pvd_conv_execute(pvd_plan* plan, const float* const* h_act, const float* h_weights, int T,
+                     const float* density, float rho_ref, float rho_min, float rho_cut, float scale, float* dose,
+                     void* stream);
+
+int pvd_plan_destroy(pvd_plan* plan);
+
+/* ---- A5/A6/A10: dose voxel kernel evaluated on the image grid ----
+ * Y90KernelGenerator.generate_kernel (data/dose_kernels/y90_kernel.py:20-55) and
+ * Lu177KernelGenerator.generate_kernel (data/dose_kernels/lu177_kernel.py:52-86), with per-axis
+ * spacing r = ||(idx - g//2) * spacing|| (the reference takes one isotropic voxel size). */
+#define PVD_NUCLIDE_Y90 0
+#define PVD_NUCLIDE_LU177 1
+typedef struct pvd_tissue {
+    float density;              /* g/cm3 */
+    float effective_Z;
+    float stopping_power_ratio;
+    float mu_by_rho;            /* cm2/g at 0.2 MeV (Lu177 gamma term) */
+    float scaling;              /* final tissue factor (Y90: y90_kernel.py:148-162; Lu177: 1) */
+} pvd_tissue;
+int pvd_kernel_eval(int nuclide, const pvd_tissue* tissue, const float spacing_mm[3], const int g[3], float* out,
+                    void* stream);
+
+/* ---- A9 helper: piecewise-linear HU -> mass density (clamped); h_knots = nk (hu, rho) pairs, nk <= 32 ---- */
+int pvd_hu_to_density_f32(const float* hu, const float* h_knots, int nk, float* rho, size_t n, void* stream);
+int pvd_hu_to_density_i16(const int16_t* hu, const float* h_knots, int nk, float* rho, size_t n, void* stream);
+
+/* ---- A3: ActivitySampler._trapezoid_integration (core/activity_sampler.py:69-79) and the missing
+ * integrate_dose_rates (core/dose_calculator.py:138): out = sum_t h_weights[t] * vol[t]. T <= 16. ---- */
+int pvd_weighted_sum(const float* const* h_vol, const float* h_weights, int T, float* out, size_t n, void* stream);
+
+/* ---- A11: TimeCurveFitting._calculate_accumulated_dose (time_integration/curve_fitting.py:74-84):
+ * out = A0 / lambda * (1 - exp(-lambda * t_limit)) elementwise. ---- */
+int pvd_monoexp_integral(const float* A0, const float* lambda, float t_limit, float* out, size_t n, void* stream);
+
+/* Standalone density scaling (same formula as the fused epilogue), in place allowed. */
+int pvd_density_scale(const float* dose, const float* density, float rho_ref, float rho_min, float rho_cut,
+                      float scale, float* out, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVDOSE_H */

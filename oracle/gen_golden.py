@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by RUNNING THE REAL REFERENCE (/root/reference) in this container.
+
+TEST INFRASTRUCTURE ONLY.  Recipe:
+  1. copy /root/reference/pyvoxeldosimetry to a writable temp dir (the factory mkdirs and
+     np.saves inside the package, data/dose_kernels/kernel_factory.py:34-35,66-73);
+  2. register permissive stub modules for the absent third-party imports (nibabel, SimpleITK,
+     pydicom, cupy, matplotlib) - the hot path never touches them;
+  3. import the real KernelConvolutionCalculator / generators / ActivitySampler and run them.
+For Lu177 the JSON `//` comments (Lu177/Lu177.json:16,21,30,32) are stripped before json.loads.
+
+The script also asserts that oracle/dose_oracle.py reproduces every generated vector (bit-exact
+for the FFT expression, <=1e-15 relative for the generators), i.e. it PINS the oracle.
+The GPU box has no /root/reference: it only reads the committed .npz files.
+
+Usage:  python oracle/gen_golden.py            (writes tests/golden/)
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+import shutil
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = "/root/reference"
+OUT = os.path.join(REPO, "tests", "golden")
+
+
+class _Stub(types.ModuleType):
+    """Permissive stand-in for an absent third-party module."""
+
+    def __getattr__(self, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        child = _Stub(f"{self.__name__}.{name}")
+        setattr(self, name, child)
+        return child
+
+    def __call__(self, *a, **k):
+        # decorators such as @cp.fuse() must hand back a callable that returns its argument
+        if len(a) == 1 and callable(a[0]) and not k:
+            return a[0]
+        return self
+
+
+def import_reference():
+    tmp = tempfile.mkdtemp(prefix="pvd_ref_")
+    shutil.copytree(os.path.join(REF, "pyvoxeldosimetry"), os.path.join(tmp, "pyvoxeldosimetry"))
+    for name in [
+        "nibabel", "nibabel.processing", "SimpleITK", "pydicom", "pydicom.dataset", "pydicom.uid",
+        "cupy", "matplotlib", "matplotlib.pyplot",
+    ]:
+        sys.modules[name] = _Stub(name)
+    # make sure our own drop-in alias package does not shadow the reference
+    sys.path = [p for p in sys.path if os.path.abspath(p or ".") != REPO]
+    for k in [k for k in sys.modules if k == "pyvoxeldosimetry" or k.startswith("pyvoxeldosimetry.")]:
+        del sys.modules[k]
+    sys.path.insert(0, tmp)
+    import pyvoxeldosimetry  # noqa: F401
+    from pyvoxeldosimetry.data.dose_kernels import base_kernel
+
+    def _load_config(self, config_path):
+        with open(config_path, "r") as f:
+            return json.loads(re.sub(r"//[^\n]*", "", f.read()))
+
+    base_kernel.BaseKernelGenerator._load_config = _load_config
+    base_kernel.BaseKernelGenerator.save_kernel = lambda self, kernel, output_dir: None  # no png/npy side effects
+    return tmp
+
+
+def main():
+    tmp = import_reference()
+    sys.path.insert(0, REPO)
+    from oracle import dose_oracle as orc
+    from pyvoxeldosimetry.core.kernel_convolution import KernelConvolutionCalculator
+    from pyvoxeldosimetry.core.activity_sampler import ActivitySampler
+    from pyvoxeldosimetry.data.dose_kernels.y90_kernel import Y90KernelGenerator
+    from pyvoxeldosimetry.data.dose_kernels.lu177_kernel import Lu177KernelGenerator
+    from pyvoxeldosimetry.time_integration.curve_fitting import TimeCurveFitting
+
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20261017)
+
+    # ---------------- kernels (A5 / A6) ----------------
+    kern = {}
+    tissues = ["water", "lung", "soft_tissue", "bone", "iodine_contrast", "no_such_tissue"]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for t in tissues:
+            for vox, grid in [(1.0, (15, 15, 15)), (2.0, (12, 10, 8)), (4.8, (9, 9, 9))]:
+                k = Y90KernelGenerator(t).generate_kernel(vox, grid)
+                key = f"Y90|{t}|{vox}|{'x'.join(map(str, grid))}"
+                kern[key] = k
+                c = tuple(g // 2 for g in grid)
+                assert np.isnan(k[c]) and np.isnan(k).sum() == 1, "reference Y90 centre is expected to be the only NaN"
+                mine = orc.y90_kernel(vox, grid, t)
+                m = np.ones(grid, bool)
+                m[c] = False
+                assert np.allclose(mine[m], k[m], rtol=1e-14, atol=0), key
+                lit = orc.y90_kernel(vox, grid, t, centre="reference")
+                assert np.isnan(lit[c])
+            for vox, grid in [(1.0, (15, 15, 15)), (4.8, (11, 11, 11)), (2.5, (8, 9, 10))]:
+                k = Lu177KernelGenerator(t).generate_kernel(vox, grid)
+                key = f"Lu177|{t}|{vox}|{'x'.join(map(str, grid))}"
+                kern[key] = k
+                assert np.isfinite(k).all()
+                assert np.allclose(orc.lu177_kernel(vox, grid, t), k, rtol=1e-14, atol=0), key
+    # scalar known answers on the production grids
+    with np.errstate(divide="ignore", invalid="ignore"):
+        k64 = Y90KernelGenerator("water").generate_kernel(1.0, (64, 64, 64))
+    kats = {
+        "y90_water_1mm_64_c+1": k64[33, 32, 32],
+        "y90_water_2mm_64_c+1": Y90KernelGenerator("water").generate_kernel(2.0, (64, 64, 64))[33, 32, 32],
+        "y90_lung_1mm_64_c+1": Y90KernelGenerator("lung").generate_kernel(1.0, (64, 64, 64))[33, 32, 32],
+        "y90_bone_1mm_64_c+1": Y90KernelGenerator("bone").generate_kernel(1.0, (64, 64, 64))[33, 32, 32],
+    }
+    l31 = Lu177KernelGenerator("water").generate_kernel(4.8, (31, 31, 31))
+    l81 = Lu177KernelGenerator("water").generate_kernel(1.0, (81, 81, 81))
+    kats.update({
+        "lu177_water_4.8mm_31_centre": l31[15, 15, 15], "lu177_water_4.8mm_31_c+1": l31[16, 15, 15],
+        "lu177_water_4.8mm_31_sum": l31.sum(), "lu177_water_1mm_81_c+1": l81[41, 40, 40], "lu177_water_1mm_81_sum": l81.sum(),
+    })
+    np.savez_compressed(os.path.join(OUT, "kernels_ref.npz"), **kern)
+
+    # ---------------- convolution through the real calculator (A1, A2) ----------------
+    calc = KernelConvolutionCalculator("Y90", "water", 1.0)  # builds (NaN-centred) 64^3 kernel
+    assert calc.kernel.shape == (64, 64, 64)
+    conv = {}
+    cases = {
+        "pad_16x12x20_k5x7x3": ((16, 12, 20), (5, 7, 3)),
+        "crop_10x9x8_k12x4x11": ((10, 9, 8), (12, 4, 11)),       # kernel larger than the grid on 2 axes
+        "odd_7x11x13_k3x3x3": ((7, 11, 13), (3, 3, 3)),          # prime lengths
+        "k1_8x8x8_k1x1x1": ((8, 8, 8), (1, 1, 1)),
+        "even_k_12x10x14_k4x6x2": ((12, 10, 14), (4, 6, 2)),
+    }
+    for name, (ashape, kshape) in cases.items():
+        a = rng.uniform(0.0, 1e3, size=ashape)
+        a[tuple(s // 2 for s in ashape)] = 2e6
+        k = rng.uniform(0.0, 1.0, size=kshape)
+        calc.kernel = k
+        d = calc.calculate_dose_rate(a, (1.0, 1.0, 1.0))
+        conv[name + "|a"], conv[name + "|k"], conv[name + "|d"] = a, k, d
+        assert np.array_equal(orc.conv_reference(a, k), d), name           # bit-exact restatement
+        bf = orc.conv_bruteforce(a, k)
+        assert orc.rel_err_of_peak(bf, d) < 1e-13, name                    # definition check
+    # multi-timepoint (A2) + activity trapezoid (A3)
+    ashape, kshape = (12, 10, 14), (5, 5, 5)
+    times = [4.0, 24.0, 96.0, 168.0]
+    a0 = rng.uniform(0.0, 1e3, size=ashape)
+    maps = [a0 * np.exp(-np.log(2) * t / 161.52) for t in times]
+    k = rng.uniform(0.0, 1.0, size=kshape)
+    calc.kernel = k
+    D = calc.calculate_absorbed_dose(maps, times, (1.0, 1.0, 1.0))
+    assert np.array_equal(orc.absorbed_dose_trapezoid(maps, times, k), D)
+    w = orc.trapezoid_weights(times, 3600.0)
+    assert orc.rel_err_of_peak(orc.conv_reference(sum(wi * m for wi, m in zip(w, maps)), k), D) < 1e-14
+    A = ActivitySampler(161.52).integrate_activity(maps, times)
+    assert np.array_equal(orc.integrate_activity_trapezoid(maps, times), A)
+    conv["tp|maps"], conv["tp|times"], conv["tp|k"], conv["tp|D"], conv["tp|A"] = np.stack(maps), np.array(times), k, D, A
+    # A11 closed-form integral
+    tcf = TimeCurveFitting(161.52)
+    params = np.stack([rng.uniform(0, 1e4, 50), rng.uniform(1e-3, 1e-1, 50)])
+    acc = tcf._calculate_accumulated_dose(params)
+    assert np.array_equal(orc.accumulated_activity_monoexp(params[0], params[1], 161.52), acc)
+    acc2 = tcf._calculate_accumulated_dose(params, integration_limit=72.0)
+    conv["a11|params"], conv["a11|acc"], conv["a11|acc72"] = params, acc, acc2
+    np.savez_compressed(os.path.join(OUT, "conv_ref.npz"), **conv)
+
+    # ---------------- config C1: the Y90 example (single_timepoint_y90_physical_decay.py) ----------------
+    sphere = orc.sphere_activity()
+    # literal reference: all-NaN because of the NaN centre voxel
+    calc2 = KernelConvolutionCalculator("Y90", "water", 1.0)
+    calc2.kernel = k64.copy()
+    with np.errstate(invalid="ignore"):
+        d_nan = calc2.calculate_dose_rate(sphere, (1.0, 1.0, 1.0))
+    kats["c1_literal_nan_voxels"] = float(np.isnan(d_nan).sum())
+    kfin = k64.copy()
+    kfin[32, 32, 32] = 1.0  # beta(0)*rho*S*f = 1 for water; brems(0) := 0
+    assert np.array_equal(orc.y90_kernel(1.0, (64, 64, 64), "water")[32, 32, 32], 1.0)
+    calc2.kernel = kfin
+    d1 = calc2.calculate_dose_rate(sphere, (1.0, 1.0, 1.0))
+    assert np.array_equal(orc.conv_reference(sphere, orc.y90_kernel(1.0, (64, 64, 64))), orc.conv_reference(sphere, kfin)) or \
+        orc.rel_err_of_peak(orc.conv_reference(sphere, orc.y90_kernel(1.0, (64, 64, 64))), d1) < 1e-14
+    kats.update({
+        "c1_sphere_voxels": float((sphere > 0).sum()), "c1_sum_a": sphere.sum(), "c1_max": d1.max(),
+        "c1_argmax": float(np.ravel_multi_index(np.unravel_index(d1.argmax(), d1.shape), d1.shape)),
+        "c1_sum": d1.sum(), "c1_d000": d1[0, 0, 0], "c1_d242424": d1[24, 24, 24], "c1_min": d1.min(),
+    })
+    # keep three orthogonal central planes through the peak (8,8,8) as array fixtures (small)
+    np.savez_compressed(os.path.join(OUT, "c1_ref.npz"), plane_x8=d1[8], plane_y8=d1[:, 8], plane_z8=d1[:, :, 8])
+    with open(os.path.join(OUT, "kats.json"), "w") as f:
+        json.dump({k: float(v) for k, v in kats.items()}, f, indent=1, sort_keys=True)
+    shutil.rmtree(tmp, ignore_errors=True)
+    print("golden written to", OUT)
+    for fn in sorted(os.listdir(OUT)):
+        print(f"  {fn}: {os.path.getsize(os.path.join(OUT, fn))} bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+"""ctypes binding of libpvdose.so (include/pvdose.h).
+
+The binding is pointer-agnostic: every array argument is an integer address.  The product hands
+it ``torch.Tensor.data_ptr()`` of CUDA tensors; there is NO CPU fallback - if the shared library
+is missing the import of the engine fails loudly (``PvdoseLibraryError``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "libpvdose.so")
+
+PVD_OK = 0
+ERR_NAMES = {-1: "PVD_ERR_INVALID", -2: "PVD_ERR_CUDA", -3: "PVD_ERR_STATE", -4: "PVD_ERR_NONFINITE", -5: "PVD_ERR_UNSUPPORTED"}
+BOUNDARY_REFERENCE, BOUNDARY_SAME = 0, 1
+ALGO_AUTO, ALGO_FFT, ALGO_DIRECT = 0, 1, 2
+MAX_T = 16
+NUCLIDE_IDS = {"Y90": 0, "Lu177": 1}
+
+# every symbol include/pvdose.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "pvd_version", "pvd_last_error", "pvd_good_fft_size", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
+    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy",
+    "pvd_kernel_eval", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
+    "pvd_density_scale",
+]
+
+
+class PvdoseLibraryError(RuntimeError):
+    pass
+
+
+class PvdoseError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [
+        ("n", C.c_int * 3), ("m", C.c_int * 3), ("out_lo", C.c_int * 3), ("out_n", C.c_int * 3), ("k", C.c_int * 3),
+        ("algo", C.c_int), ("passes", C.c_int), ("workspace_bytes", C.c_size_t), ("hbm_bytes_per_execute", C.c_double),
+    ]
+
+
+class Tissue(C.Structure):
+    _fields_ = [("density", C.c_float), ("effective_Z", C.c_float), ("stopping_power_ratio", C.c_float),
+                ("mu_by_rho", C.c_float), ("scaling", C.c_float)]
+
+
+def _i3(v: Sequence[int]):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+class PvdLib:
+    """Thin, typed view of the shared library."""
+
+    def __init__(self, path: Optional[str] = None):
+        path = path or os.environ.get("PVDOSE_LIB", DEFAULT_LIB)
+        if not os.path.exists(path):
+            raise PvdoseLibraryError(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback for the dose path."
+            )
+        try:
+            self.dll = C.CDLL(path)
+        except OSError as e:  # pragma: no cover
+            raise PvdoseLibraryError(f"cannot load {path}: {e}") from e
+        self.path = path
+        d = self.dll
+        vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+        d.pvd_version.restype = C.c_int
+        d.pvd_last_error.restype = C.c_char_p
+        d.pvd_good_fft_size.argtypes = [C.c_int]
+        d.pvd_plan_create.argtypes = [C.POINTER(vp), ip, ip, C.c_int, C.c_int]
+        d.pvd_plan_create_ex.argtypes = [C.POINTER(vp), ip, ip, ip, ip, ip, C.c_int]
+        d.pvd_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
+        d.pvd_plan_workspace_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+        d.pvd_plan_set_workspace.argtypes = [vp, vp, C.c_size_t, vp]
+        d.pvd_plan_set_kernel.argtypes = [vp, vp, vp]
+        d.pvd_conv_execute.argtypes = [vp, C.POINTER(vp), fp, C.c_int, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
+        d.pvd_plan_destroy.argtypes = [vp]
+        d.pvd_kernel_eval.argtypes = [C.c_int, C.POINTER(Tissue), fp, ip, vp, vp]
+        d.pvd_hu_to_density_f32.argtypes = [vp, fp, C.c_int, vp, C.c_size_t, vp]
+        d.pvd_hu_to_density_i16.argtypes = [vp, fp, C.c_int, vp, C.c_size_t, vp]
+        d.pvd_weighted_sum.argtypes = [C.POINTER(vp), fp, C.c_int, vp, C.c_size_t, vp]
+        d.pvd_monoexp_integral.argtypes = [vp, vp, C.c_float, vp, C.c_size_t, vp]
+        d.pvd_density_scale.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, C.c_size_t, vp]
+
+    # ------------------------------------------------------------------ helpers
+    def check(self, rc: int):
+        if rc != PVD_OK:
+            raise PvdoseError(rc, (self.dll.pvd_last_error() or b"").decode())
+
+    def version(self) -> int:
+        return self.dll.pvd_version()
+
+    def good_fft_size(self, n: int) -> int:
+        return self.dll.pvd_good_fft_size(int(n))
+
+    def plan_create(self, n, k, boundary: int, algo: int = ALGO_AUTO) -> int:
+        h = C.c_void_p()
+        self.check(self.dll.pvd_plan_create(C.byref(h), _i3(n), _i3(k), boundary, algo))
+        return h.value
+
+    def plan_create_ex(self, n, m, out_lo, out_n, k, algo: int = ALGO_AUTO) -> int:
+        h = C.c_void_p()
+        self.check(self.dll.pvd_plan_create_ex(C.byref(h), _i3(n), _i3(m), _i3(out_lo), _i3(out_n), _i3(k), algo))
+        return h.value
+
+    def plan_info(self, plan: int) -> PlanInfo:
+        info = PlanInfo()
+        self.check(self.dll.pvd_plan_get_info(plan, C.byref(info)))
+        return info
+
+    def plan_workspace_bytes(self, plan: int) -> int:
+        b = C.c_size_t()
+        self.check(self.dll.pvd_plan_workspace_bytes(plan, C.byref(b)))
+        return b.value
+
+    def plan_set_workspace(self, plan: int, ptr: int, nbytes: int, stream: int = 0):
+        self.check(self.dll.pvd_plan_set_workspace(plan, ptr, nbytes, stream))
+
+    def plan_set_kernel(self, plan: int, kernel_ptr: int, stream: int = 0):
+        self.check(self.dll.pvd_plan_set_kernel(plan, kernel_ptr, stream))
+
+    def conv_execute(self, plan: int, act_ptrs: Sequence[int], weights: Optional[Sequence[float]], density_ptr: Optional[int],
+                     rho_ref: float, rho_min: float, rho_cut: float, scale: float, dose_ptr: int, stream: int = 0):
+        T = len(act_ptrs)
+        ptrs = (C.c_void_p * T)(*act_ptrs)
+        w = (C.c_float * T)(*[float(x) for x in weights]) if weights is not None else None
+        self.check(self.dll.pvd_conv_execute(plan, ptrs, w, T, density_ptr, rho_ref, rho_min, rho_cut, scale, dose_ptr, stream))
+
+    def plan_destroy(self, plan: int):
+        self.dll.pvd_plan_destroy(plan)
+
+    def kernel_eval(self, nuclide_id: int, tissue: Tissue, spacing, grid, out_ptr: int, stream: int = 0):
+        sp = (C.c_float * 3)(*[float(s) for s in spacing])
+        self.check(self.dll.pvd_kernel_eval(nuclide_id, C.byref(tissue), sp, _i3(grid), out_ptr, stream))
+
+    def hu_to_density(self, hu_ptr: int, is_i16: bool, knots, rho_ptr: int, n: int, stream: int = 0):
+        flat = [float(v) for pair in knots for v in pair]
+        arr = (C.c_float * len(flat))(*flat)
+        fn = self.dll.pvd_hu_to_density_i16 if is_i16 else self.dll.pvd_hu_to_density_f32
+        self.check(fn(hu_ptr, arr, len(flat) // 2, rho_ptr, n, stream))
+
+    def weighted_sum(self, vol_ptrs: Sequence[int], weights: Sequence[float], out_ptr: int, n: int, stream: int = 0):
+        T = len(vol_ptrs)
+        ptrs = (C.c_void_p * T)(*vol_ptrs)
+        w = (C.c_float * T)(*[float(x) for x in weights])
+        self.check(self.dll.pvd_weighted_sum(ptrs, w, T, out_ptr, n, stream))
+
+    def monoexp_integral(self, a0_ptr: int, lam_ptr: int, t_limit: float, out_ptr: int, n: int, stream: int = 0):
+        self.check(self.dll.pvd_monoexp_integral(a0_ptr, lam_ptr, t_limit, out_ptr, n, stream))
+
+    def density_scale(self, dose_ptr: int, den_ptr: int, rho_ref: float, rho_min: float, rho_cut: float, scale: float,
+                      out_ptr: int, n: int, stream: int = 0):
+        self.check(self.dll.pvd_density_scale(dose_ptr, den_ptr, rho_ref, rho_min, rho_cut, scale, out_ptr, n, stream))
+
+
+_LIB: Optional[PvdLib] = None
+
+
+def get_lib() -> PvdLib:
+    """The process-wide product library (libpvdose.so next to this file)."""
+    global _LIB
+    if _LIB is None:
+        _LIB = PvdLib()
+    return _LIB

@@ -1,0 +1,102 @@
+// Bandwidth-bound elementwise kernels of the dose path: dose-voxel-kernel evaluation on the image
+// grid (A5/A6/A10), HU -> density (A9), time-weighted accumulation (A3), closed-form mono-exponential
+// integral (A11) and the standalone density scale.
+#pragma once
+#include "pvd_common.cuh"
+
+namespace pvd {
+
+// Radial dose-point-kernel model shared by the Y90 and Lu177 generators:
+//   k(r) = scaling * [ sum_b amp_b (1 - r/R_b)^2 exp(-2 r / R_b) [r <= R_b]
+//                      + sum_p amp_p exp(-mu_p r / 10) / (4 pi r^2) [r > 0] ]
+struct RadialModel {
+    int nb, np;
+    double beta_range[4], beta_amp[4];
+    double phot_mu[4], phot_amp[4];
+    double scaling;
+    double sp[3];
+    int g[3];
+};
+
+__global__ void kernel_eval_kernel(const RadialModel m, float* out) {
+    const long long n = (long long)m.g[0] * m.g[1] * m.g[2];
+    const int c0 = m.g[0] / 2, c1 = m.g[1] / 2, c2 = m.g[2] / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % m.g[2]);
+        const long long t = i / m.g[2];
+        const int y = (int)(t % m.g[1]);
+        const int x = (int)(t / m.g[1]);
+        const double dx = (x - c0) * m.sp[0], dy = (y - c1) * m.sp[1], dz = (z - c2) * m.sp[2];
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        double v = 0.0;
+        for (int b = 0; b < m.nb; ++b) {
+            if (r <= m.beta_range[b]) {
+                const double u = 1.0 - r / m.beta_range[b];
+                v += m.beta_amp[b] * (u * u * exp(-2.0 * r / m.beta_range[b]));
+            }
+        }
+        if (r > 0.0) {
+            for (int p = 0; p < m.np; ++p)
+                v += m.phot_amp[p] * exp(-m.phot_mu[p] * r / 10.0) / (4.0 * 3.141592653589793 * (r * r));
+        }
+        out[i] = (float)(v * m.scaling);
+    }
+}
+
+struct Knots {
+    int nk;
+    float hu[32], rho[32];
+};
+
+template <class T>
+__global__ void hu_to_density_kernel(const T* __restrict__ hu, const Knots k, float* __restrict__ rho, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float h = (float)hu[i];
+        float r;
+        if (h <= k.hu[0]) {
+            r = k.rho[0];
+        } else if (h >= k.hu[k.nk - 1]) {
+            r = k.rho[k.nk - 1];
+        } else {
+            int j = 1;
+            while (h > k.hu[j]) ++j;
+            const float t = (h - k.hu[j - 1]) / (k.hu[j] - k.hu[j - 1]);
+            r = k.rho[j - 1] + t * (k.rho[j] - k.rho[j - 1]);
+        }
+        rho[i] = r;
+    }
+}
+
+struct WsumArgs {
+    const float* v[kMaxT];
+    float w[kMaxT];
+    int T;
+};
+
+__global__ void weighted_sum_kernel(const WsumArgs a, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < a.T; ++t) acc += a.w[t] * __ldg(a.v[t] + i);
+        out[i] = acc;
+    }
+}
+
+__global__ void monoexp_integral_kernel(const float* __restrict__ A0, const float* __restrict__ lam, float tlim,
+                                        float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float l = lam[i];
+        // -expm1(-x) keeps full relative precision for small lambda*T
+        out[i] = A0[i] / l * (-expm1f(-l * tlim));
+    }
+}
+
+__global__ void density_scale_kernel(const float* __restrict__ dose, const float* __restrict__ den, float rho_ref,
+                                     float rho_min, float rho_cut, float scale, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float rho = den[i];
+        const float v = dose[i] * scale;
+        out[i] = (rho < rho_cut) ? 0.f : v * (rho_ref / fmaxf(rho, rho_min));
+    }
+}
+
+}  // namespace pvd

@@ -1,0 +1,132 @@
+// Common definitions for the pvdose CUDA sources.
+//
+// The product is compiled by nvcc for sm_100a.  The same sources also compile with plain g++
+// when PVD_EMULATE is defined: a tiny SIMT emulator (one std::thread per CUDA thread, a
+// std::barrier for __syncthreads) that exists ONLY so the index logic of every kernel can be
+// exercised by the CPU test-suite in a container that has no GPU.  The emulated library is
+// test infrastructure (built into tests/_emu/, never loaded by the package).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+
+#ifdef PVD_EMULATE
+// ------------------------------------------------------------------ CPU emulation of SIMT
+#include <barrier>
+#include <functional>
+#include <thread>
+#include <vector>
+#include <cstdlib>
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static
+#define PVD_UNROLL
+
+namespace pvd_emu {
+struct Ctx {
+    dim3 tid, bid, bdim, gdim;
+    std::barrier<>* bar = nullptr;
+    char* smem = nullptr;
+};
+inline thread_local Ctx ctx;
+}  // namespace pvd_emu
+#define threadIdx (pvd_emu::ctx.tid)
+#define blockIdx (pvd_emu::ctx.bid)
+#define blockDim (pvd_emu::ctx.bdim)
+#define gridDim (pvd_emu::ctx.gdim)
+static inline void __syncthreads() { pvd_emu::ctx.bar->arrive_and_wait(); }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline void sincospi(double x, double* s, double* c) {
+    *s = std::sin(M_PI * x);
+    *c = std::cos(M_PI * x);
+}
+#define PVD_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(pvd_emu::ctx.smem)
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaPeekAtLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+
+namespace pvd_emu {
+template <class K, class... Args>
+void launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
+    const unsigned T = block.x * block.y * block.z;
+    std::vector<char> smem(smem_bytes + 64);
+    std::barrier<> bar((std::ptrdiff_t)T);
+    auto worker = [&](unsigned t) {
+        Ctx& c = ctx;
+        c.bdim = block;
+        c.gdim = grid;
+        c.bar = &bar;
+        c.smem = smem.data();
+        c.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+        for (unsigned bz = 0; bz < grid.z; ++bz)
+            for (unsigned by = 0; by < grid.y; ++by)
+                for (unsigned bx = 0; bx < grid.x; ++bx) {
+                    c.bid = dim3(bx, by, bz);
+                    kernel(args...);
+                    bar.arrive_and_wait();  // block boundary: smem is reused by the next block
+                }
+    };
+    std::vector<std::thread> th;
+    th.reserve(T);
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& x : th) x.join();
+}
+}  // namespace pvd_emu
+#define PVD_LAUNCH(kernel, grid, block, smem, stream, ...) pvd_emu::launch(kernel, grid, block, smem, __VA_ARGS__)
+#define PVD_SET_SMEM(kernel, bytes) (0)
+static constexpr int PVD_BLOCK = 32;  // small blocks keep the emulator fast; kernels are block-size agnostic
+
+#else
+// ------------------------------------------------------------------ real CUDA
+#include <cuda_runtime.h>
+#define PVD_UNROLL _Pragma("unroll")
+#define PVD_DYN_SMEM(T, name)                                         \
+    extern __shared__ __align__(16) unsigned char pvd_dyn_smem_raw[]; \
+    T* name = reinterpret_cast<T*>(pvd_dyn_smem_raw)
+#define PVD_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define PVD_SET_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+static constexpr int PVD_BLOCK = 256;
+#endif
+
+namespace pvd {
+
+static constexpr int kMaxStages = 16;
+static constexpr int kMaxT = 16;  // activity volumes fused into one first-pass load
+
+struct Stages {
+    int n;
+    int radix[kMaxStages];
+};
+
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+}  // namespace pvd

@@ -1,0 +1,535 @@
+// libpvdose: plan management and the C ABI (include/pvdose.h).
+#include "../../include/pvdose.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "elementwise.cuh"
+#include "fft_passes.cuh"
+
+using namespace pvd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define PVD_CUDA_CHECK(what)                                                                  \
+    do {                                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) return fail(PVD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e__)); \
+    } while (0)
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- radix schedule -------------------------------------------------------------------------
+bool make_stages(int M, Stages& st) {
+    st.n = 0;
+    if (M < 1) return false;
+    std::vector<int> r;
+    int m = M, e2 = 0;
+    while (m % 2 == 0) {
+        m /= 2;
+        ++e2;
+    }
+    int e3 = 0, e5 = 0, e7 = 0;
+    while (m % 3 == 0) { m /= 3; ++e3; }
+    while (m % 5 == 0) { m /= 5; ++e5; }
+    while (m % 7 == 0) { m /= 7; ++e7; }
+    for (; e5 >= 2; e5 -= 2) r.push_back(25);
+    if (e5) r.push_back(5);
+    for (; e3 >= 2; e3 -= 2) r.push_back(9);
+    if (e3) r.push_back(3);
+    for (; e7 > 0; --e7) r.push_back(7);
+    for (int p = 11; m > 1; p += 2) {  // remaining primes -> generic O(p^2) stage
+        while (m % p == 0) {
+            r.push_back(p);
+            m /= p;
+        }
+        if ((long long)p * p > m && m > 1) {
+            r.push_back(m);
+            m = 1;
+        }
+    }
+    if (e2 > 0) {
+        const int nst = (e2 + 3) / 4;
+        const int base = e2 / nst, rem = e2 % nst;
+        for (int i = 0; i < nst; ++i) r.push_back(1 << (base + (i < rem ? 1 : 0)));
+    }
+    if ((int)r.size() > kMaxStages) return false;
+    st.n = (int)r.size();
+    for (int i = 0; i < st.n; ++i) st.radix[i] = r[i];
+    return true;
+}
+
+bool is_smooth7(int m) {
+    for (int p : {2, 3, 5, 7})
+        while (m % p == 0) m /= p;
+    return m == 1;
+}
+
+double size_cost(int m) {
+    Stages st;
+    if (!make_stages(m, st)) return 1e30;
+    return (double)m * (3.0 + st.n);
+}
+
+int good_size(int n) {
+    if (n <= 1) return 1;
+    int best = -1;
+    double bc = 1e30;
+    for (int m = n; m <= 2 * n; ++m) {
+        if (!is_smooth7(m)) continue;
+        const double c = size_cost(m);
+        if (c < bc) {
+            bc = c;
+            best = m;
+        }
+        if ((double)m * 4.0 > bc) break;  // no later candidate can win
+    }
+    return best;
+}
+
+int ilog2_floor(int v) {
+    int l = 0;
+    while ((1 << (l + 1)) <= v) ++l;
+    return l;
+}
+
+}  // namespace
+
+struct pvd_plan {
+    int n[3], m[3], olo[3], on[3], k[3], ke[3];
+    int Nh, Sz;
+    int algo;
+    Stages st[3];
+    int rowLlog, colWlog[2];          // tile shapes
+    size_t rowSmem, colSmem[2];
+    size_t off_tw[3], off_buf, off_spec, off_flag, ws_bytes;
+    char* ws = nullptr;
+    bool kernel_set = false;
+    float2* tw(int a) const { return reinterpret_cast<float2*>(ws + off_tw[a]); }
+    float2* buf() const { return reinterpret_cast<float2*>(ws + off_buf); }
+    float2* spec() const { return reinterpret_cast<float2*>(ws + off_spec); }
+    int* flag() const { return reinterpret_cast<int*>(ws + off_flag); }
+};
+
+namespace {
+
+int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, int T, long long s0, long long s1,
+                    const int ext[3], cudaStream_t stream) {
+    RowFwdArgs a;
+    memset(&a, 0, sizeof a);
+    for (int t = 0; t < T; ++t) {
+        a.in[t] = in[t];
+        a.w[t] = w ? w[t] : 1.0f;
+    }
+    a.T = T;
+    a.in_s0 = s0;
+    a.in_s1 = s1;
+    a.n0 = ext[0];
+    a.n1 = ext[1];
+    a.n2 = ext[2];
+    a.out = p->buf();
+    a.out_s0 = (long long)p->m[1] * p->Sz;
+    a.out_s1 = p->Sz;
+    a.M2 = p->m[2];
+    a.Nh = p->Nh;
+    a.Llog = p->rowLlog;
+    a.tw = p->tw(2);
+    a.st = p->st[2];
+    const long long nrows = (long long)ext[0] * ext[1];
+    const long long per = 2LL << p->rowLlog;
+    const long long nblk = (nrows + per - 1) / per;
+    if (nblk <= 0) return PVD_OK;
+    PVD_LAUNCH(rows_fwd_kernel, dim3((unsigned)nblk), dim3(PVD_BLOCK), p->rowSmem, stream, a);
+    PVD_CUDA_CHECK("rows_fwd_kernel");
+    return PVD_OK;
+}
+
+int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2* out, int outer0, int nouter,
+                int n_in, int out_lo, int out_n, float scale, cudaStream_t stream) {
+    ColArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = in;
+    a.out = out;
+    a.spec = p->spec();
+    const long long plane = (long long)p->m[1] * p->Sz;
+    a.es = axis == 0 ? plane : p->Sz;
+    a.os = axis == 0 ? p->Sz : plane;
+    a.outer0 = outer0;
+    a.n_in = n_in;
+    a.M = p->m[axis];
+    a.out_lo = out_lo;
+    a.out_n = out_n;
+    a.nzf = p->Nh;
+    a.Wlog = p->colWlog[axis];
+    a.mode = mode;
+    a.scale = scale;
+    a.tw = p->tw(axis);
+    a.st = p->st[axis];
+    const int W = 1 << a.Wlog;
+    if (nouter <= 0) return PVD_OK;
+    PVD_LAUNCH(cols_kernel, dim3((unsigned)((p->Nh + W - 1) / W), (unsigned)nouter), dim3(PVD_BLOCK), p->colSmem[axis],
+               stream, a);
+    PVD_CUDA_CHECK("cols_kernel");
+    return PVD_OK;
+}
+
+int plan_finish(pvd_plan* p) {
+    for (int i = 0; i < 3; ++i) {
+        if (p->n[i] < 1 || p->k[i] < 1 || p->on[i] < 1 || p->olo[i] < 0)
+            return fail(PVD_ERR_INVALID, "axis %d: extents must be positive (n=%d k=%d out_n=%d out_lo=%d)", i, p->n[i],
+                        p->k[i], p->on[i], p->olo[i]);
+        if (p->m[i] < p->n[i] || p->olo[i] + p->on[i] > p->m[i])
+            return fail(PVD_ERR_INVALID, "axis %d: transform extent %d too small for n=%d / output [%d,%d)", i, p->m[i],
+                        p->n[i], p->olo[i], p->olo[i] + p->on[i]);
+        p->ke[i] = std::min(p->k[i], p->m[i]);
+        if (!make_stages(p->m[i], p->st[i])) return fail(PVD_ERR_UNSUPPORTED, "axis %d: cannot factor length %d", i, p->m[i]);
+    }
+    p->Nh = p->m[2] / 2 + 1;
+    p->Sz = (int)align_up((size_t)p->Nh, 16);
+    // rows: 2^Llog complex lines, smem = 2 buffers * M2 * (L+1) float2
+    {
+        int Llog = 4;
+        auto smem = [&](int l) { return 2 * (size_t)p->m[2] * ((1u << l) + 1) * sizeof(float2); };
+        while (Llog > 0 && smem(Llog) > 114 * 1024) --Llog;
+        if (smem(Llog) > kMaxSmem) return fail(PVD_ERR_UNSUPPORTED, "axis 2 length %d exceeds the shared-memory engine", p->m[2]);
+        p->rowLlog = Llog;
+        p->rowSmem = smem(Llog);
+    }
+    for (int a = 0; a < 2; ++a) {
+        int Wlog = 4;
+        auto smem = [&](int l) { return 2 * (size_t)p->m[a] * (1u << l) * sizeof(float2); };
+        while (Wlog > 0 && smem(Wlog) > 72 * 1024) --Wlog;
+        if (smem(Wlog) > kMaxSmem) return fail(PVD_ERR_UNSUPPORTED, "axis %d length %d exceeds the shared-memory engine", a, p->m[a]);
+        p->colWlog[a] = Wlog;
+        p->colSmem[a] = smem(Wlog);
+    }
+    size_t off = 0;
+    for (int a = 0; a < 3; ++a) {
+        p->off_tw[a] = off;
+        off = align_up(off + (size_t)p->m[a] * sizeof(float2), 256);
+    }
+    const size_t vol = (size_t)p->m[0] * p->m[1] * p->Sz * sizeof(float2);
+    p->off_buf = off;
+    off = align_up(off + vol, 256);
+    p->off_spec = off;
+    off = align_up(off + vol, 256);
+    p->off_flag = off;
+    off = align_up(off + 256, 256);
+    p->ws_bytes = off;
+    p->algo = PVD_ALGO_FFT;
+    return PVD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pvd_version(void) { return PVD_VERSION; }
+const char* pvd_last_error(void) { return g_err.c_str(); }
+int pvd_good_fft_size(int n) { return good_size(n); }
+
+int pvd_plan_create_ex(pvd_plan** out, const int n[3], const int m[3], const int out_lo[3], const int out_n[3],
+                       const int k[3], int algo) {
+    if (!out || !n || !out_lo || !out_n || !k) return fail(PVD_ERR_INVALID, "null argument");
+    if (algo == PVD_ALGO_DIRECT) return fail(PVD_ERR_UNSUPPORTED, "direct algorithm not available in this build");
+    pvd_plan* p = new pvd_plan();
+    for (int i = 0; i < 3; ++i) {
+        p->n[i] = n[i];
+        p->k[i] = k[i];
+        p->olo[i] = out_lo[i];
+        p->on[i] = out_n[i];
+        p->m[i] = (m && m[i] > 0) ? m[i] : good_size(std::max(n[i], out_lo[i] + out_n[i]));
+    }
+    int rc = plan_finish(p);
+    if (rc != PVD_OK) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return PVD_OK;
+}
+
+int pvd_plan_create(pvd_plan** out, const int n[3], const int k[3], int boundary, int algo) {
+    if (!out || !n || !k) return fail(PVD_ERR_INVALID, "null argument");
+    int m[3], lo[3], on[3];
+    for (int i = 0; i < 3; ++i) {
+        if (n[i] < 1 || k[i] < 1) return fail(PVD_ERR_INVALID, "axis %d: n=%d k=%d must be positive", i, n[i], k[i]);
+        on[i] = n[i];
+        if (boundary == PVD_BOUNDARY_REFERENCE) {
+            m[i] = n[i];
+            lo[i] = 0;
+        } else if (boundary == PVD_BOUNDARY_SAME) {
+            const int c = k[i] / 2;
+            lo[i] = c;
+            m[i] = good_size(std::max(std::max(n[i] + k[i] - 1 - c, k[i]), n[i] + c));
+        } else {
+            return fail(PVD_ERR_INVALID, "unknown boundary mode %d", boundary);
+        }
+    }
+    return pvd_plan_create_ex(out, n, m, lo, on, k, algo);
+}
+
+int pvd_plan_get_info(const pvd_plan* p, pvd_plan_info* info) {
+    if (!p || !info) return fail(PVD_ERR_INVALID, "null argument");
+    for (int i = 0; i < 3; ++i) {
+        info->n[i] = p->n[i];
+        info->m[i] = p->m[i];
+        info->out_lo[i] = p->olo[i];
+        info->out_n[i] = p->on[i];
+        info->k[i] = p->k[i];
+    }
+    info->algo = p->algo;
+    info->passes = 5;
+    info->workspace_bytes = p->ws_bytes;
+    const double c = 8.0 * p->Nh;  // bytes of one half-spectrum row
+    const double real_in = 4.0 * p->n[0] * p->n[1] * p->n[2];
+    const double real_out = 4.0 * p->on[0] * p->on[1] * p->on[2];
+    double b = real_in + c * p->n[0] * p->n[1];                                   // P1
+    b += c * p->n[0] * (p->n[1] + p->m[1]);                                       // P2
+    b += c * p->m[1] * ((double)p->n[0] + p->m[0] + p->on[0]);                    // P3 (+ spectrum)
+    b += c * p->on[0] * ((double)p->m[1] + p->on[1]);                             // P4
+    b += c * p->on[0] * p->on[1] + 2.0 * real_out;                                // P5 (+ density)
+    info->hbm_bytes_per_execute = b;
+    return PVD_OK;
+}
+
+int pvd_plan_workspace_bytes(const pvd_plan* p, size_t* bytes) {
+    if (!p || !bytes) return fail(PVD_ERR_INVALID, "null argument");
+    *bytes = p->ws_bytes;
+    return PVD_OK;
+}
+
+int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* stream_) {
+    if (!p || !workspace) return fail(PVD_ERR_INVALID, "null argument");
+    if (bytes < p->ws_bytes) return fail(PVD_ERR_INVALID, "workspace too small: %zu < %zu", bytes, p->ws_bytes);
+    if ((uintptr_t)workspace % 256 != 0) return fail(PVD_ERR_INVALID, "workspace must be 256-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    p->ws = (char*)workspace;
+    p->kernel_set = false;
+    for (int a = 0; a < 3; ++a) {
+        PVD_LAUNCH(twiddle_kernel, dim3((unsigned)std::min(64, (p->m[a] + 127) / 128)), dim3(128), 0, stream, p->tw(a),
+                   p->m[a]);
+        PVD_CUDA_CHECK("twiddle_kernel");
+    }
+    if (PVD_SET_SMEM(rows_fwd_kernel, kMaxSmem) != 0 || PVD_SET_SMEM(rows_inv_kernel, kMaxSmem) != 0 ||
+        PVD_SET_SMEM(cols_kernel, kMaxSmem) != 0) {
+        cudaGetLastError();
+        return fail(PVD_ERR_CUDA, "cannot opt in to %zu bytes of dynamic shared memory", kMaxSmem);
+    }
+    return PVD_OK;
+}
+
+int pvd_plan_set_kernel(pvd_plan* p, const float* kernel, void* stream_) {
+    if (!p || !kernel) return fail(PVD_ERR_INVALID, "null argument");
+    if (!p->ws) return fail(PVD_ERR_STATE, "workspace not set");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    p->kernel_set = false;
+    const long long nk = (long long)p->k[0] * p->k[1] * p->k[2];
+    cudaMemsetAsync(p->flag(), 0, sizeof(int), stream);
+    PVD_LAUNCH(finite_check_kernel, dim3((unsigned)std::min<long long>(1024, (nk + 255) / 256)), dim3(256), 0, stream,
+               kernel, nk, p->flag());
+    PVD_CUDA_CHECK("finite_check_kernel");
+    int bad = 0;
+    cudaMemcpyAsync(&bad, p->flag(), sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) {
+        PVD_CUDA_CHECK("finite check");
+        return fail(PVD_ERR_CUDA, "finite check: stream synchronise failed");
+    }
+    if (bad) return fail(PVD_ERR_NONFINITE, "dose kernel contains non-finite values");
+    const float* in[1] = {kernel};
+    int rc = launch_rows_fwd(p, in, nullptr, 1, (long long)p->k[1] * p->k[2], p->k[2], p->ke, stream);
+    if (rc) return rc;
+    rc = launch_cols(p, 1, COL_FWD, p->buf(), p->buf(), 0, p->ke[0], p->ke[1], 0, p->m[1], 1.f, stream);
+    if (rc) return rc;
+    const float norm = (float)(1.0 / ((double)p->m[0] * p->m[1] * p->m[2]));
+    rc = launch_cols(p, 0, COL_SPEC, p->buf(), p->spec(), 0, p->m[1], p->ke[0], 0, p->m[0], norm, stream);
+    if (rc) return rc;
+    p->kernel_set = true;
+    return PVD_OK;
+}
+
+int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, const float* density,
+                     float rho_ref, float rho_min, float rho_cut, float scale, float* dose, void* stream_) {
+    if (!p || !h_act || !dose) return fail(PVD_ERR_INVALID, "null argument");
+    if (T < 1 || T > PVD_MAX_T) return fail(PVD_ERR_INVALID, "T=%d outside [1,%d]: pre-accumulate with pvd_weighted_sum", T, PVD_MAX_T);
+    if (!p->ws) return fail(PVD_ERR_STATE, "workspace not set");
+    if (!p->kernel_set) return fail(PVD_ERR_STATE, "dose kernel not set");
+    for (int t = 0; t < T; ++t)
+        if (!h_act[t]) return fail(PVD_ERR_INVALID, "activity pointer %d is null", t);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = launch_rows_fwd(p, h_act, h_weights, T, (long long)p->n[1] * p->n[2], p->n[2], p->n, stream);
+    if (rc) return rc;
+    rc = launch_cols(p, 1, COL_FWD, p->buf(), p->buf(), 0, p->n[0], p->n[1], 0, p->m[1], 1.f, stream);
+    if (rc) return rc;
+    rc = launch_cols(p, 0, COL_CONV, p->buf(), p->buf(), 0, p->m[1], p->n[0], p->olo[0], p->on[0], 1.f, stream);
+    if (rc) return rc;
+    rc = launch_cols(p, 1, COL_INV, p->buf(), p->buf(), p->olo[0], p->on[0], p->m[1], p->olo[1], p->on[1], 1.f, stream);
+    if (rc) return rc;
+    RowInvArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = p->buf();
+    a.in_s0 = (long long)p->m[1] * p->Sz;
+    a.in_s1 = p->Sz;
+    a.x_lo = p->olo[0];
+    a.y_lo = p->olo[1];
+    a.z_lo = p->olo[2];
+    a.O0 = p->on[0];
+    a.O1 = p->on[1];
+    a.O2 = p->on[2];
+    a.out = dose;
+    a.out_s0 = (long long)p->on[1] * p->on[2];
+    a.out_s1 = p->on[2];
+    a.density = density;
+    a.den_s0 = a.out_s0;
+    a.den_s1 = a.out_s1;
+    a.rho_ref = rho_ref;
+    a.rho_min = rho_min;
+    a.rho_cut = rho_cut;
+    a.scale = scale;
+    a.M2 = p->m[2];
+    a.Nh = p->Nh;
+    a.Llog = p->rowLlog;
+    a.tw = p->tw(2);
+    a.st = p->st[2];
+    const long long nrows = (long long)p->on[0] * p->on[1];
+    const long long per = 2LL << p->rowLlog;
+    PVD_LAUNCH(rows_inv_kernel, dim3((unsigned)((nrows + per - 1) / per)), dim3(PVD_BLOCK), p->rowSmem, stream, a);
+    PVD_CUDA_CHECK("rows_inv_kernel");
+    return PVD_OK;
+}
+
+int pvd_plan_destroy(pvd_plan* p) {
+    delete p;
+    return PVD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static unsigned ew_grid(size_t n) { return (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16); }
+
+int pvd_kernel_eval(int nuclide, const pvd_tissue* t, const float spacing[3], const int g[3], float* out, void* stream) {
+    if (!t || !spacing || !g || !out) return fail(PVD_ERR_INVALID, "null argument");
+    if (g[0] < 1 || g[1] < 1 || g[2] < 1) return fail(PVD_ERR_INVALID, "grid extents must be positive");
+    RadialModel m;
+    memset(&m, 0, sizeof m);
+    const double rho = t->density, S = t->stopping_power_ratio;
+    if (nuclide == PVD_NUCLIDE_Y90) {
+        // data/dose_kernels/y90_kernel.py:93-140, Y90/Y90.json:22
+        m.nb = 1;
+        m.beta_range[0] = 11.0 * std::pow(2.280, 1.5) * (1.0 / rho) * (1.0 / S);
+        m.beta_amp[0] = rho * S;
+        m.np = 1;
+        const double ry = (t->effective_Z / 7.42) * (t->effective_Z / 7.42);
+        m.phot_mu[0] = 0.096 * (rho / 1.0);
+        m.phot_amp[0] = 0.015 * ry * rho;
+    } else if (nuclide == PVD_NUCLIDE_LU177) {
+        // data/dose_kernels/lu177_kernel.py:129-184, Lu177/Lu177.json:21-26
+        const double E[3] = {0.498, 0.385, 0.177}, ab[3] = {0.795, 0.089, 0.116};
+        m.nb = 3;
+        for (int i = 0; i < 3; ++i) {
+            m.beta_range[i] = 5.0 * std::pow(E[i], 1.5) * (1.0 / rho) * (1.0 / S);
+            m.beta_amp[i] = ab[i] * rho * S;
+        }
+        const double Eg[2] = {0.208, 0.113}, Ig[2] = {0.111, 0.062};
+        m.np = 2;
+        for (int i = 0; i < 2; ++i) {
+            m.phot_mu[i] = rho * t->mu_by_rho * std::pow(0.2 / Eg[i], 3.2);
+            m.phot_amp[i] = Ig[i];
+        }
+    } else {
+        return fail(PVD_ERR_INVALID, "unknown nuclide id %d", nuclide);
+    }
+    m.scaling = t->scaling;
+    for (int i = 0; i < 3; ++i) {
+        m.sp[i] = spacing[i];
+        m.g[i] = g[i];
+    }
+    const size_t n = (size_t)g[0] * g[1] * g[2];
+    PVD_LAUNCH(kernel_eval_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, m, out);
+    PVD_CUDA_CHECK("kernel_eval_kernel");
+    return PVD_OK;
+}
+
+static int fill_knots(const float* h_knots, int nk, Knots& k) {
+    if (!h_knots || nk < 2 || nk > 32) return fail(PVD_ERR_INVALID, "need 2..32 (hu, rho) knots");
+    k.nk = nk;
+    for (int i = 0; i < nk; ++i) {
+        k.hu[i] = h_knots[2 * i];
+        k.rho[i] = h_knots[2 * i + 1];
+        if (i && !(k.hu[i] > k.hu[i - 1])) return fail(PVD_ERR_INVALID, "HU knots must be strictly increasing");
+    }
+    return PVD_OK;
+}
+
+int pvd_hu_to_density_f32(const float* hu, const float* h_knots, int nk, float* rho, size_t n, void* stream) {
+    Knots k;
+    if (int rc = fill_knots(h_knots, nk, k)) return rc;
+    if (!hu || !rho) return fail(PVD_ERR_INVALID, "null argument");
+    if (n == 0) return PVD_OK;
+    PVD_LAUNCH(hu_to_density_kernel<float>, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, hu, k, rho, n);
+    PVD_CUDA_CHECK("hu_to_density_kernel");
+    return PVD_OK;
+}
+
+int pvd_hu_to_density_i16(const int16_t* hu, const float* h_knots, int nk, float* rho, size_t n, void* stream) {
+    Knots k;
+    if (int rc = fill_knots(h_knots, nk, k)) return rc;
+    if (!hu || !rho) return fail(PVD_ERR_INVALID, "null argument");
+    if (n == 0) return PVD_OK;
+    PVD_LAUNCH(hu_to_density_kernel<int16_t>, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, hu, k, rho, n);
+    PVD_CUDA_CHECK("hu_to_density_kernel");
+    return PVD_OK;
+}
+
+int pvd_weighted_sum(const float* const* h_vol, const float* h_weights, int T, float* out, size_t n, void* stream) {
+    if (!h_vol || !out) return fail(PVD_ERR_INVALID, "null argument");
+    if (T < 1 || T > PVD_MAX_T) return fail(PVD_ERR_INVALID, "T=%d outside [1,%d]", T, PVD_MAX_T);
+    WsumArgs a;
+    memset(&a, 0, sizeof a);
+    a.T = T;
+    for (int t = 0; t < T; ++t) {
+        if (!h_vol[t]) return fail(PVD_ERR_INVALID, "volume pointer %d is null", t);
+        a.v[t] = h_vol[t];
+        a.w[t] = h_weights ? h_weights[t] : 1.f;
+    }
+    if (n == 0) return PVD_OK;
+    PVD_LAUNCH(weighted_sum_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, a, out, n);
+    PVD_CUDA_CHECK("weighted_sum_kernel");
+    return PVD_OK;
+}
+
+int pvd_monoexp_integral(const float* A0, const float* lambda, float t_limit, float* out, size_t n, void* stream) {
+    if (!A0 || !lambda || !out) return fail(PVD_ERR_INVALID, "null argument");
+    if (n == 0) return PVD_OK;
+    PVD_LAUNCH(monoexp_integral_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, A0, lambda, t_limit, out, n);
+    PVD_CUDA_CHECK("monoexp_integral_kernel");
+    return PVD_OK;
+}
+
+int pvd_density_scale(const float* dose, const float* density, float rho_ref, float rho_min, float rho_cut, float scale,
+                      float* out, size_t n, void* stream) {
+    if (!dose || !density || !out) return fail(PVD_ERR_INVALID, "null argument");
+    if (n == 0) return PVD_OK;
+    PVD_LAUNCH(density_scale_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, dose, density, rho_ref, rho_min,
+               rho_cut, scale, out, n);
+    PVD_CUDA_CHECK("density_scale_kernel");
+    return PVD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+"""Device-side engine: torch tensors for memory/streams, libpvdose (CUDA, sm_100a) for the arithmetic.
+
+PyTorch is plumbing here (device memory, streams, pinned staging, torch.distributed); every
+number is produced by the hand-written kernels behind the C ABI.  No CPU fallback: without a
+CUDA device or without libpvdose.so the constructors raise.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import ALGO_AUTO, BOUNDARY_REFERENCE, BOUNDARY_SAME, MAX_T, PvdoseError, get_lib
+
+BOUNDARY_IDS = {"reference": BOUNDARY_REFERENCE, "circular": BOUNDARY_REFERENCE, "same": BOUNDARY_SAME, "zero": BOUNDARY_SAME}
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "pyvoxeldosimetry_b200 needs a CUDA device (B200, sm_100a): the kernel-convolution dose path has no CPU fallback"
+        )
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    if dev.type != "cuda":
+        raise RuntimeError(f"device {dev} is not a CUDA device")
+    return dev
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def to_device_f32(x, device: torch.device) -> torch.Tensor:
+    """Host ndarray / tensor -> contiguous float32 CUDA tensor (no copy when already there)."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        a = np.asarray(x)
+        if a.dtype != np.float32:
+            a = a.astype(np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+class ConvPlan:
+    """A reusable convolution plan: transform sizes, workspace, cached kernel spectrum.
+
+    ``boundary='reference'`` reproduces core/kernel_convolution.py:71-74 (circular, origin-anchored
+    kernel); ``boundary='same'`` is the zero-boundary, centred variant.  ``ex`` gives the expert
+    geometry (slab decomposition): dict(m=, out_lo=, out_n=).
+    """
+
+    def __init__(self, shape: Sequence[int], kshape: Sequence[int], boundary: str = "reference", device=None,
+                 algo: int = ALGO_AUTO, ex: Optional[dict] = None):
+        self.device = require_cuda(device)
+        self.lib = get_lib()
+        self.shape = tuple(int(s) for s in shape)
+        self.kshape = tuple(int(s) for s in kshape)
+        if len(self.shape) != 3 or len(self.kshape) != 3:
+            raise ValueError("activity and kernel must be 3-D")
+        self.boundary = boundary
+        with torch.cuda.device(self.device):
+            if ex is not None:
+                self.handle = self.lib.plan_create_ex(self.shape, ex.get("m", (0, 0, 0)), ex["out_lo"], ex["out_n"], self.kshape, algo)
+            else:
+                if boundary not in BOUNDARY_IDS:
+                    raise ValueError(f"unknown boundary mode {boundary!r} (use 'reference' or 'same')")
+                self.handle = self.lib.plan_create(self.shape, self.kshape, BOUNDARY_IDS[boundary], algo)
+            self.info = self.lib.plan_info(self.handle)
+            self.out_shape = tuple(self.info.out_n)
+            self.fft_shape = tuple(self.info.m)
+            nbytes = self.lib.plan_workspace_bytes(self.handle)
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.lib.plan_set_workspace(self.handle, self.workspace.data_ptr(), nbytes, _stream_ptr(self.device))
+        self._kernel_dev: Optional[torch.Tensor] = None
+
+    # -------------------------------------------------------------- kernel
+    def set_kernel(self, kernel) -> None:
+        k = to_device_f32(kernel, self.device)
+        if tuple(k.shape) != self.kshape:
+            raise ValueError(f"kernel shape {tuple(k.shape)} does not match the plan {self.kshape}")
+        with torch.cuda.device(self.device):
+            self.lib.plan_set_kernel(self.handle, k.data_ptr(), _stream_ptr(self.device))
+        self._kernel_dev = k
+
+    # -------------------------------------------------------------- execute (device resident)
+    def execute(self, acts: Sequence[torch.Tensor], weights: Optional[Sequence[float]] = None,
+                density: Optional[torch.Tensor] = None, rho_ref: float = 1.0, rho_min: float = 0.1,
+                rho_cut: float = 0.0, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """dose = scale * conv(sum_t w_t act_t, kernel) [* rho_ref / max(rho, rho_min)] - all tensors on device."""
+        if len(acts) < 1:
+            raise ValueError("No activity maps provided")
+        for a in acts:
+            if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous() or tuple(a.shape) != self.shape:
+                raise ValueError("activity tensors must be contiguous float32 CUDA tensors of the plan shape")
+        if density is not None and (density.device != self.device or density.dtype != torch.float32
+                                    or not density.is_contiguous() or tuple(density.shape) != self.out_shape):
+            raise ValueError("density must be a contiguous float32 CUDA tensor of the output shape")
+        if out is None:
+            out = torch.empty(self.out_shape, dtype=torch.float32, device=self.device)
+        acts = list(acts)
+        w = None if weights is None else [float(x) for x in weights]
+        with torch.cuda.device(self.device):
+            stream = _stream_ptr(self.device)
+            if len(acts) > MAX_T:  # fold the tail into one volume first (linearity)
+                if w is None:
+                    w = [1.0] * len(acts)
+                acc = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+                first = True
+                while len(acts) > MAX_T - 1:
+                    chunk, cw = acts[: MAX_T - 1], w[: MAX_T - 1]
+                    acts, w = acts[MAX_T - 1:], w[MAX_T - 1:]
+                    ptrs, ws = [c.data_ptr() for c in chunk], list(cw)
+                    if not first:
+                        ptrs.append(acc.data_ptr())
+                        ws.append(1.0)
+                    self.lib.weighted_sum(ptrs, ws, acc.data_ptr(), acc.numel(), stream)
+                    first = False
+                acts, w = acts + [acc], w + [1.0]
+            self.lib.conv_execute(self.handle, [a.data_ptr() for a in acts], w,
+                                  None if density is None else density.data_ptr(),
+                                  rho_ref, rho_min, rho_cut, scale, out.data_ptr(), stream)
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PlanCache:
+    """Plans keyed by (shape, kshape, boundary, device); the kernel spectrum is rebuilt only when the
+    kernel content changes (the reference recomputes fftn(kernel) on every call)."""
+
+    def __init__(self, capacity: int = 4):
+        self.capacity = capacity
+        self._plans: Dict[tuple, ConvPlan] = {}
+        self._kernel_tag: Dict[tuple, object] = {}
+        self._lock = threading.Lock()
+
+    def get(self, shape, kshape, boundary, device, kernel_tag, kernel_provider) -> ConvPlan:
+        key = (tuple(shape), tuple(kshape), boundary, str(device))
+        with self._lock:
+            plan = self._plans.get(key)
+            if plan is None:
+                while len(self._plans) >= self.capacity:
+                    old_key = next(iter(self._plans))
+                    self._plans.pop(old_key).close()
+                    self._kernel_tag.pop(old_key, None)
+                plan = ConvPlan(shape, kshape, boundary, device)
+                self._plans[key] = plan
+            if self._kernel_tag.get(key) != kernel_tag:
+                plan.set_kernel(kernel_provider())
+                self._kernel_tag[key] = kernel_tag
+            return plan
+
+    def clear(self):
+        with self._lock:
+            for p in self._plans.values():
+                p.close()
+            self._plans.clear()
+            self._kernel_tag.clear()
+
+
+# ---------------------------------------------------------------------------- elementwise ops
+def kernel_eval(nuclide: str, tissue_props: dict, spacing: Sequence[float], grid: Sequence[int], device=None) -> torch.Tensor:
+    dev = require_cuda(device)
+    lib = get_lib()
+    if nuclide not in _capi.NUCLIDE_IDS:
+        raise ValueError(f"no device generator for {nuclide}")
+    t = _capi.Tissue(tissue_props["density"], tissue_props["effective_Z"], tissue_props["stopping_power_ratio"],
+                     tissue_props.get("mu_by_rho", 0.0), tissue_props.get("scaling", 1.0))
+    out = torch.empty(tuple(int(g) for g in grid), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        lib.kernel_eval(_capi.NUCLIDE_IDS[nuclide], t, spacing, grid, out.data_ptr(), _stream_ptr(dev))
+    return out
+
+
+def hu_to_density(hu: torch.Tensor, knots) -> torch.Tensor:
+    dev = require_cuda(hu.device)
+    if hu.dtype not in (torch.int16, torch.float32):
+        hu = hu.to(torch.float32)
+    hu = hu.contiguous()
+    rho = torch.empty(hu.shape, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        get_lib().hu_to_density(hu.data_ptr(), hu.dtype == torch.int16, knots, rho.data_ptr(), hu.numel(), _stream_ptr(dev))
+    return rho
+
+
+def weighted_sum(vols: Sequence[torch.Tensor], weights: Sequence[float]) -> torch.Tensor:
+    dev = require_cuda(vols[0].device)
+    out = torch.empty_like(vols[0])
+    lib = get_lib()
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(dev)
+        vols, weights = list(vols), [float(w) for w in weights]
+        first = True
+        while vols:
+            take = MAX_T if first else MAX_T - 1
+            chunk, cw = vols[:take], weights[:take]
+            vols, weights = vols[take:], weights[take:]
+            ptrs, ws = [c.data_ptr() for c in chunk], list(cw)
+            if not first:
+                ptrs.append(out.data_ptr())
+                ws.append(1.0)
+            lib.weighted_sum(ptrs, ws, out.data_ptr(), out.numel(), stream)
+            first = False
+    return out
+
+
+def monoexp_integral(A0: torch.Tensor, lam: torch.Tensor, t_limit: float) -> torch.Tensor:
+    dev = require_cuda(A0.device)
+    out = torch.empty_like(A0)
+    with torch.cuda.device(dev):
+        get_lib().monoexp_integral(A0.data_ptr(), lam.data_ptr(), float(t_limit), out.data_ptr(), A0.numel(), _stream_ptr(dev))
+    return out
+
+
+def density_scale(dose: torch.Tensor, density: torch.Tensor, rho_ref=1.0, rho_min=0.1, rho_cut=0.0, scale=1.0) -> torch.Tensor:
+    dev = require_cuda(dose.device)
+    out = torch.empty_like(dose)
+    with torch.cuda.device(dev):
+        get_lib().density_scale(dose.data_ptr(), density.data_ptr(), rho_ref, rho_min, rho_cut, scale, out.data_ptr(),
+                                dose.numel(), _stream_ptr(dev))
+    return out

@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the kernel-convolution dose path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1] [--boundary reference|same]
+
+A *step* is one pass of the hot path over one synthetic patient volume per GPU:
+  workload c3 (default, the configuration the metric is quoted on): 512x512x400 float32 activity,
+  Y90/water 51^3 dose voxel kernel @ 1 mm, voxel-wise density correction, reference boundary mode.
+Rank 0 prints ONE JSON line.  `value` = whole-job dose volumes/s with inputs resident in HBM;
+`e2e` = the same through the public Python calculator API with pinned HOST buffers (H2D + D2H inside
+the timed region).  N > 1 (torchrun, one rank per GPU, NCCL): independent volumes are sharded over the
+ranks with no data-path collective (weak scaling).  `--impl reference` times the reference's own CPU
+path (the literal np.fft expression of core/kernel_convolution.py:71-74, single-threaded by
+construction) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (shape, kernel grid, nuclide, voxel mm, T, density)
+    "c3": dict(shape=(512, 512, 400), kgrid=(51, 51, 51), nuclide="Y90", voxel=1.0, T=1, density=True,
+               desc="C3: Y90 whole-body 512x512x400, 51^3 DVK @1mm, density-corrected"),
+    "c2": dict(shape=(256, 256, 256), kgrid=(31, 31, 31), nuclide="Lu177", voxel=4.8, T=4, density=False,
+               desc="C2: Lu-177 4-timepoint time-integrated dose 256^3, 31^3 DVK @4.8mm"),
+    "c1": dict(shape=(48, 48, 48), kgrid=(64, 64, 64), nuclide="Y90", voxel=1.0, T=1, density=False,
+               desc="C1: examples/single_timepoint_y90_physical_decay.py 48^3, 64^3 DVK"),
+}
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def synth_inputs(wl, seed=90):
+    """Synthetic activity / density of SURVEY.md section 8d (fixed seed), float32."""
+    rng = np.random.default_rng(seed)
+    n0, n1, n2 = wl["shape"]
+    acts = []
+    base = rng.uniform(0.0, 1e2, size=wl["shape"]).astype(np.float32)
+    sl = tuple(slice(int(n * 0.39), int(n * 0.39) + max(1, int(n * 0.2))) for n in wl["shape"])
+    base[sl] = 2e6
+    times = [4.0, 24.0, 96.0, 168.0][: wl["T"]] if wl["T"] > 1 else [2.0]
+    for t in times:
+        acts.append(base if wl["T"] == 1 else (base * np.float32(np.exp(-np.log(2) * t / 161.52))).astype(np.float32))
+    rho = None
+    if wl["density"]:
+        x = (np.arange(n0, dtype=np.float32) - n0 / 2) / (0.42 * n0)
+        y = (np.arange(n1, dtype=np.float32) - n1 / 2) / (0.30 * n1)
+        body = (x[:, None] ** 2 + y[None, :] ** 2) <= 1.0
+        lung = (((x[:, None] - 0.45) / 0.3) ** 2 + (y[None, :] / 0.5) ** 2 <= 1.0) | (((x[:, None] + 0.45) / 0.3) ** 2 + (y[None, :] / 0.5) ** 2 <= 1.0)
+        spine = (x[:, None] ** 2 + ((y[None, :] - 0.6) ** 2)) <= 0.02
+        plane = np.full((n0, n1), 0.00129, dtype=np.float32)
+        plane[body] = 1.04
+        plane[lung & body] = 0.26
+        plane[spine] = 1.42
+        rho = np.ascontiguousarray(np.broadcast_to(plane[:, :, None], wl["shape"])).astype(np.float32)
+    return acts, times, rho
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        hot = sorted(sm)[len(sm) // 2:] if sm else []  # upper half ~ samples under load
+        return {"sm_mhz": statistics.median(hot) if hot else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_time(wl, budget_s: float, acts, rho, kernel64):
+    """Literal reference operator (oracle.conv_reference == core/kernel_convolution.py:71-74, float64,
+    single-threaded np.fft) on a bounded sub-volume of the workload.  Returns (voxels/s, sample text, seconds)."""
+    from oracle import dose_oracle as orc
+
+    full = wl["shape"]
+    cands = [full]
+    s = list(full)
+    for ax in (2, 1, 0, 2, 1, 0):
+        s = list(s)
+        s[ax] = max(8, s[ax] // 2)
+        cands.append(tuple(s))
+    # calibrate on the smallest candidate
+    small = cands[-1]
+    a = acts[0][: small[0], : small[1], : small[2]].astype(np.float64)
+    t0 = time.perf_counter()
+    orc.conv_reference(a, kernel64)
+    rate = a.size / (time.perf_counter() - t0)  # voxels/s, optimistic for the bigger ones
+    pick = small
+    for c in cands:
+        if np.prod(c) / rate * 1.6 <= budget_s:
+            pick = c
+            break
+    a = np.ascontiguousarray(acts[0][: pick[0], : pick[1], : pick[2]]).astype(np.float64)
+    t0 = time.perf_counter()
+    d = orc.conv_reference(a, kernel64)
+    if rho is not None:
+        d = orc.density_correct(d, rho[: pick[0], : pick[1], : pick[2]])
+    dt = time.perf_counter() - t0
+    return a.size / dt, f"literal np.fft.ifftn(fftn(a)*fftn(k,a.shape)).real float64 on a {pick[0]}x{pick[1]}x{pick[2]} sub-volume", dt
+
+
+def run_reference(args, wl):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from oracle import dose_oracle as orc
+
+    acts, times, rho = synth_inputs(wl)
+    k64 = orc.make_kernel(wl["nuclide"], wl["voxel"], wl["kgrid"]).astype(np.float32).astype(np.float64)
+    nvox = float(np.prod(wl["shape"]))
+    total_budget = 150.0
+    per = total_budget / max(1, args.steps + args.warmup)
+    rate, sample, dt = cpu_reference_time(wl, per, acts, rho, k64)  # also serves as warm-up / calibration
+    pick = tuple(int(x) for x in sample.split(" on a ")[1].split(" ")[0].split("x"))
+    a = np.ascontiguousarray(acts[0][: pick[0], : pick[1], : pick[2]]).astype(np.float64)
+    r = None if rho is None else rho[: pick[0], : pick[1], : pick[2]]
+    for _ in range(max(0, args.warmup - 1)):
+        orc.conv_reference(a, k64)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d = orc.conv_reference(a, k64)
+        if r is not None:
+            d = orc.density_correct(d, r)
+    dt = (time.perf_counter() - t0) / args.steps
+    vps = a.size / dt
+    value = vps / nvox
+    line = {
+        "impl": "reference", "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": vps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * nvox / a.size,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "boundary": args.boundary, "note": "volumes/s = measured voxels/s on the sample / voxels per volume"},
+        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": 1, "kind": "port", "sample": sample + f", {args.steps} steps; np.fft is single-threaded"},
+        "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the dose path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=dev)
+    from pyvoxeldosimetry_b200 import KernelConvolutionCalculator
+    from pyvoxeldosimetry_b200.engine import ConvPlan
+
+    peak_gbs, peak_src = peaks()
+    acts_h, times, rho_h = synth_inputs(wl, seed=90 + rank)
+    calc = KernelConvolutionCalculator(wl["nuclide"], "water", wl["voxel"],
+                                       config={"kernel_grid": wl["kgrid"], "boundary": args.boundary, "device": str(dev)})
+    kdev = calc._kernel_dev
+    plan = ConvPlan(wl["shape"], wl["kgrid"], args.boundary, dev)
+    plan.set_kernel(kdev)
+    acts = [torch.from_numpy(a).to(dev) for a in acts_h]
+    rho = None if rho_h is None else torch.from_numpy(rho_h).to(dev)
+    out = torch.empty(plan.out_shape, dtype=torch.float32, device=dev)
+    w = None
+    if wl["T"] > 1:
+        from pyvoxeldosimetry_b200.core import trapezoid_weights
+
+        w = trapezoid_weights(times, 3600.0)
+    nvox = float(np.prod(wl["shape"]))
+
+    def step():
+        plan.execute(acts, w, rho, out=out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    # per-kernel device times (CUDA events recorded by the library around each launch), separate pass
+    plan.lib.plan_set_profiling(plan.handle, True)
+    acc = None
+    prof_iters = 5
+    for _ in range(prof_iters):
+        step()
+        pt = plan.lib.plan_get_pass_times(plan.handle)
+        if acc is None:
+            acc = [[n, 0.0, b] for (n, _, b) in pt]
+        for i, (_, ms, _) in enumerate(pt):
+            acc[i][1] += ms / prof_iters
+    plan.lib.plan_set_profiling(plan.handle, False)
+    # ---- timed region: K steps, device resident
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * 1e3 / ms_step  # volumes/s, whole job
+
+    # ---- e2e through the public calculator API with pinned host buffers
+    pin_acts = [torch.from_numpy(a).pin_memory() for a in acts_h]
+    pin_rho = None if rho_h is None else torch.from_numpy(rho_h).pin_memory()
+    pin_out = torch.empty(plan.out_shape, dtype=torch.float32).pin_memory()
+    vox = (wl["voxel"],) * 3
+
+    def e2e_step():
+        if wl["T"] == 1:
+            return calc.calculate_dose_rate(pin_acts[0], vox, tissue_densities=pin_rho, out=pin_out)
+        return calc.calculate_absorbed_dose(pin_acts, times, vox, tissue_densities=pin_rho, out=pin_out)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world / float(t.item())
+    h2d = int(sum(a.numel() for a in pin_acts) * 4 + (pin_rho.numel() * 4 if pin_rho is not None else 0))
+    d2h = int(pin_out.numel() * 4)
+
+    if rank == 0:
+        alg_bytes = 4.0 * (wl["T"] + 1 + (1 if wl["density"] else 0)) * nvox
+        info = plan.info
+        kernels = [{"name": n, "ms": round(ms, 4), "hbm_bytes": b, "gbs": round(b / ms / 1e6, 1) if ms > 0 else None,
+                    "frac_of_peak": round(b / ms / 1e6 / peak_gbs, 3) if ms > 0 else None} for (n, ms, b) in (acc or [])]
+        ksum = sum(k["ms"] for k in kernels) or ms_step
+        dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox,
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "boundary": args.boundary, "fft_shape": list(plan.fft_shape),
+                       "volumes_per_step_per_gpu": 1, "l2": "inputs (>=419 MB per volume for c3) exceed the 126 MB L2",
+                       "parallelism": f"independent volumes sharded over {world} rank(s), no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
+                         "frac": round(achieved / peak_gbs, 4), "traffic": None,
+                         "what": "whole conv path (all launches of one volume): algorithmic 4*(T+1+[density]) B/voxel / time per volume",
+                         "peak_source": peak_src, "algorithmic_bytes_per_volume": alg_bytes,
+                         "implementation_bytes_per_volume": info.hbm_bytes_per_execute,
+                         "implementation_gbs": round(info.hbm_bytes_per_execute / (ms_step * 1e-3) / 1e9, 1),
+                         "dominant_kernel": dom, "dominant_share_of_step": round(dom["ms"] / ksum, 3) if dom else None},
+            "kernels": kernels,
+            "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": dt * 1e3, "api": "KernelConvolutionCalculator.calculate_dose_rate(host ndarray, tissue_densities=host ndarray)"},
+            "gpu_launches": int(info.passes) * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import dose_oracle as orc
+
+            k64 = calc.kernel.astype(np.float32).astype(np.float64)
+            rate, sample, secs = cpu_reference_time(wl, 20.0, acts_h, rho_h, k64)
+            line["cpu_baseline"] = {"value": rate / nvox, "unit": "volumes/s", "cores": 1, "kind": "port",
+                                    "sample": sample + f" ({secs:.1f} s); np.fft is single-threaded", "host_cores_available": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--boundary", default="reference", choices=["reference", "same"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,21 +106,37 @@ int pvd_conv_execute(pvd_plan* plan, const float* const* h_act, const float* h_w
 
 int pvd_plan_destroy(pvd_plan* plan);
 
+/* Measurement hook (bench.py / profiles): when enabled, every pvd_conv_execute brackets each of its
+ * kernel launches with CUDA events on the execute stream.  pvd_plan_get_pass_times synchronises the
+ * last recorded events and returns the per-launch durations (ms) and the bytes each launch moves
+ * through HBM by construction; names[i] points to a static string.  Returns the number of launches. */
+#define PVD_MAX_PASSES 8
+int pvd_plan_set_profiling(pvd_plan* plan, int enable);
+int pvd_plan_get_pass_times(pvd_plan* plan, float* ms, double* hbm_bytes, const char** names, int cap);
+
 /* ---- A5/A6/A10: dose voxel kernel evaluated on the image grid ----
- * Y90KernelGenerator.generate_kernel (data/dose_kernels/y90_kernel.py:20-55) and
- * Lu177KernelGenerator.generate_kernel (data/dose_kernels/lu177_kernel.py:52-86), with per-axis
- * spacing r = ||(idx - g//2) * spacing|| (the reference takes one isotropic voxel size). */
-#define PVD_NUCLIDE_Y90 0
-#define PVD_NUCLIDE_LU177 1
-typedef struct pvd_tissue {
-    float density;              /* g/cm3 */
-    float effective_Z;
-    float stopping_power_ratio;
-    float mu_by_rho;            /* cm2/g at 0.2 MeV (Lu177 gamma term) */
-    float scaling;              /* final tissue factor (Y90: y90_kernel.py:148-162; Lu177: 1) */
-} pvd_tissue;
-int pvd_kernel_eval(int nuclide, const pvd_tissue* tissue, const float spacing_mm[3], const int g[3], float* out,
-                    void* stream);
+ * Device evaluation of the radial dose-point-kernel form shared by the reference's generators
+ * (Y90KernelGenerator.generate_kernel data/dose_kernels/y90_kernel.py:20-55,93-140;
+ *  Lu177KernelGenerator.generate_kernel data/dose_kernels/lu177_kernel.py:52-86,129-184;
+ *  Ga68KernelGenerator data/dose_kernels/ga68_kernel.py:20-83):
+ *    k(r) = scaling * [ sum_b beta_amp[b] (1 - r/beta_range[b])^2 exp(-2 r/beta_range[b]) [r <= beta_range[b]]
+ *                       + sum_p phot_amp[p] exp(-phot_mu[p] r / 10) / (4 pi r^2) [r > 0] ]
+ * on a [g0][g1][g2] grid centred at g//2 with per-axis spacing r = ||(idx - g//2) * spacing_mm||
+ * (the reference takes one isotropic voxel size; per-axis spacing is the A10 extension).  Arithmetic is
+ * float64 on the device, output float32.  The photon term is 0 at r = 0 (the reference yields NaN there
+ * for Y90/Ga68; Lu177 masks it the same way, lu177_kernel.py:176-182).  The nuclide/tissue constants
+ * live in the host-side generators, as they do in the reference. */
+#define PVD_RADIAL_MAX_TERMS 4
+typedef struct pvd_radial_model {
+    int n_beta, n_photon;
+    double beta_range[PVD_RADIAL_MAX_TERMS]; /* mm */
+    double beta_amp[PVD_RADIAL_MAX_TERMS];
+    double phot_mu[PVD_RADIAL_MAX_TERMS];    /* 1/cm */
+    double phot_amp[PVD_RADIAL_MAX_TERMS];
+    double scaling;
+} pvd_radial_model;
+int pvd_kernel_eval_radial(const pvd_radial_model* model, const double spacing_mm[3], const int g[3], float* out,
+                           void* stream);
 
 /* ---- A9 helper: piecewise-linear HU -> mass density (clamped); h_knots = nk (hu, rho) pairs, nk <= 32 ---- */
 int pvd_hu_to_density_f32(const float* hu, const float* h_knots, int nk, float* rho, size_t n, void* stream);

@@ -354,20 +354,26 @@ def conv_reference_slabbed(activity: np.ndarray, kernel: np.ndarray, world: int,
 
 
 def conv_same_slabbed(activity: np.ndarray, kernel: np.ndarray, world: int) -> np.ndarray:
-    """'same' mode computed slab by slab: c0 = K0//2 planes from below and K0-1-c0 from above,
-    zeros beyond the volume ends.  Must equal conv_same(activity, kernel)."""
+    """'same' mode computed slab by slab: d[g] = sum_t k[t] a[g + c0 - t] needs K0-1-c0 planes from below
+    and c0 = K0//2 planes from above (zeros beyond the volume ends); the interior sits at full-convolution
+    index K0-1 of the local problem.  Must equal conv_same(activity, kernel)."""
     a = np.asarray(activity, dtype=np.float64)
     k = np.asarray(kernel, dtype=np.float64)
     n0 = a.shape[0]
-    c0 = k.shape[0] // 2
-    up = k.shape[0] - 1 - c0
+    K0 = k.shape[0]
+    c0 = K0 // 2
+    dn = K0 - 1 - c0
+    c1, c2 = k.shape[1] // 2, k.shape[2] // 2
     out = np.empty_like(a)
     for lo, hi in slab_bounds(n0, world):
-        local = np.zeros((hi - lo + c0 + up,) + a.shape[1:], dtype=np.float64)
-        src_lo, src_hi = max(lo - c0, 0), min(hi + up, n0)
-        local[src_lo - (lo - c0) : src_hi - (lo - c0)] = a[src_lo:src_hi]
-        d = conv_same(local, k)
-        out[lo:hi] = d[c0 : c0 + (hi - lo)]
+        local = np.zeros((hi - lo + K0 - 1,) + a.shape[1:], dtype=np.float64)
+        src_lo, src_hi = max(lo - dn, 0), min(hi + c0, n0)
+        local[src_lo - (lo - dn) : src_hi - (lo - dn)] = a[src_lo:src_hi]
+        big = tuple(n + kk - 1 for n, kk in zip(local.shape, k.shape))
+        pad = np.zeros(big)
+        pad[: local.shape[0], : local.shape[1], : local.shape[2]] = local
+        full = conv_reference(pad, k)
+        out[lo:hi] = full[K0 - 1 : K0 - 1 + (hi - lo), c1 : c1 + a.shape[1], c2 : c2 + a.shape[2]]
     return out
 
 

@@ -18,13 +18,12 @@ ERR_NAMES = {-1: "PVD_ERR_INVALID", -2: "PVD_ERR_CUDA", -3: "PVD_ERR_STATE", -4:
 BOUNDARY_REFERENCE, BOUNDARY_SAME = 0, 1
 ALGO_AUTO, ALGO_FFT, ALGO_DIRECT = 0, 1, 2
 MAX_T = 16
-NUCLIDE_IDS = {"Y90": 0, "Lu177": 1}
 
 # every symbol include/pvdose.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "pvd_version", "pvd_last_error", "pvd_good_fft_size", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
-    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy",
-    "pvd_kernel_eval", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
+    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times",
+    "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
     "pvd_density_scale",
 ]
 
@@ -46,9 +45,9 @@ class PlanInfo(C.Structure):
     ]
 
 
-class Tissue(C.Structure):
-    _fields_ = [("density", C.c_float), ("effective_Z", C.c_float), ("stopping_power_ratio", C.c_float),
-                ("mu_by_rho", C.c_float), ("scaling", C.c_float)]
+class RadialModel(C.Structure):
+    _fields_ = [("n_beta", C.c_int), ("n_photon", C.c_int), ("beta_range", C.c_double * 4), ("beta_amp", C.c_double * 4),
+                ("phot_mu", C.c_double * 4), ("phot_amp", C.c_double * 4), ("scaling", C.c_double)]
 
 
 def _i3(v: Sequence[int]):
@@ -83,7 +82,9 @@ class PvdLib:
         d.pvd_plan_set_kernel.argtypes = [vp, vp, vp]
         d.pvd_conv_execute.argtypes = [vp, C.POINTER(vp), fp, C.c_int, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
         d.pvd_plan_destroy.argtypes = [vp]
-        d.pvd_kernel_eval.argtypes = [C.c_int, C.POINTER(Tissue), fp, ip, vp, vp]
+        d.pvd_plan_set_profiling.argtypes = [vp, C.c_int]
+        d.pvd_plan_get_pass_times.argtypes = [vp, fp, C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.c_int]
+        d.pvd_kernel_eval_radial.argtypes = [C.POINTER(RadialModel), C.POINTER(C.c_double), ip, vp, vp]
         d.pvd_hu_to_density_f32.argtypes = [vp, fp, C.c_int, vp, C.c_size_t, vp]
         d.pvd_hu_to_density_i16.argtypes = [vp, fp, C.c_int, vp, C.c_size_t, vp]
         d.pvd_weighted_sum.argtypes = [C.POINTER(vp), fp, C.c_int, vp, C.c_size_t, vp]
@@ -137,9 +138,30 @@ class PvdLib:
     def plan_destroy(self, plan: int):
         self.dll.pvd_plan_destroy(plan)
 
-    def kernel_eval(self, nuclide_id: int, tissue: Tissue, spacing, grid, out_ptr: int, stream: int = 0):
-        sp = (C.c_float * 3)(*[float(s) for s in spacing])
-        self.check(self.dll.pvd_kernel_eval(nuclide_id, C.byref(tissue), sp, _i3(grid), out_ptr, stream))
+    def plan_set_profiling(self, plan: int, enable: bool):
+        self.check(self.dll.pvd_plan_set_profiling(plan, 1 if enable else 0))
+
+    def plan_get_pass_times(self, plan: int):
+        """-> [(name, ms, hbm_bytes)] of the last execute (synchronises its events)."""
+        cap = 8
+        ms, by, names = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_char_p * cap)()
+        n = self.dll.pvd_plan_get_pass_times(plan, ms, by, names, cap)
+        if n < 0:
+            self.check(n)
+        return [(names[i].decode(), float(ms[i]), float(by[i])) for i in range(n)]
+
+    def kernel_eval_radial(self, beta_terms, photon_terms, scaling: float, spacing, grid, out_ptr: int, stream: int = 0):
+        """beta_terms: [(range_mm, amplitude)], photon_terms: [(mu_per_cm, amplitude)]."""
+        m = RadialModel()
+        m.n_beta, m.n_photon, m.scaling = len(beta_terms), len(photon_terms), float(scaling)
+        if m.n_beta > 4 or m.n_photon > 4:
+            raise ValueError("at most 4 beta and 4 photon terms")
+        for i, (r, a) in enumerate(beta_terms):
+            m.beta_range[i], m.beta_amp[i] = float(r), float(a)
+        for i, (mu, a) in enumerate(photon_terms):
+            m.phot_mu[i], m.phot_amp[i] = float(mu), float(a)
+        sp = (C.c_double * 3)(*[float(s) for s in spacing])
+        self.check(self.dll.pvd_kernel_eval_radial(C.byref(m), sp, _i3(grid), out_ptr, stream))
 
     def hu_to_density(self, hu_ptr: int, is_i16: bool, knots, rho_ptr: int, n: int, stream: int = 0):
         flat = [float(v) for pair in knots for v in pair]

@@ -1,0 +1,173 @@
+"""KernelConvolutionCalculator - drop-in for the reference class of the same name
+(core/kernel_convolution.py:26-115) with the arithmetic on the GPU.
+
+Reference semantics kept by default:
+  * calculate_dose_rate == np.fft.ifftn(fftn(a) * fftn(kernel, a.shape)).real (kernel_convolution.py:71-74):
+    circular over the activity grid, kernel anchored at the origin  -> ``boundary='reference'``;
+  * calculate_absorbed_dose == trapezoid of the per-timepoint dose rates, hours -> seconds
+    (kernel_convolution.py:94-106), evaluated as ONE convolution of sum_i w_i a_i (linearity);
+  * the kernel is the factory's 64^3 grid at ``kernel_resolution`` (kernel_convolution.py:39-46).
+Config keys (all optional): boundary ('reference'|'same'), kernel_grid, device, output_dtype
+('float32'|'float64'), rho_ref, rho_min, rho_cut, scale, strict_reference.
+Repairs over the reference are listed in SURVEY.md section 8b; `strict_reference=True` turns the
+behavioural ones off (the resample stub then raises instead of crashing with AttributeError).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import engine
+from ..data.dose_kernels.kernel_factory import KernelFactory
+from .dosimetry_base import DosimetryCalculator
+
+HOURS_TO_SECONDS = 3600.0  # kernel_convolution.py:102
+
+
+def trapezoid_weights(time_points: Sequence[float], unit_factor: float = 1.0) -> List[float]:
+    """Weights w_i with sum_i w_i f(t_i) == the reference's trapezoid loops
+    (kernel_convolution.py:101-104 with unit_factor=3600; activity_sampler.py:74-78 with 1)."""
+    t = [float(x) for x in time_points]
+    w = [0.0] * len(t)
+    for i in range(len(t) - 1):
+        d = (t[i + 1] - t[i]) * unit_factor
+        w[i] += d / 2
+        w[i + 1] += d / 2
+    return w
+
+
+def _same_spacing(voxel_size, res: float) -> bool:
+    v = np.asarray(voxel_size, dtype=np.float64).reshape(-1)
+    return v.size == 3 and bool(np.all(np.abs(v - res) <= 1e-9 * max(1.0, abs(res))))
+
+
+class KernelConvolutionCalculator(DosimetryCalculator):
+    def __init__(self, radionuclide: str, tissue_name: str, kernel_resolution: float = 1.0,
+                 config: Optional[Dict[str, Any]] = None):
+        super().__init__(radionuclide, tissue_name, config)
+        self.device = engine.require_cuda(self.config.get("device"))
+        self.kernel_factory = KernelFactory()
+        self.kernel_resolution = kernel_resolution
+        self.tissue_name = tissue_name
+        self.boundary = self.config.get("boundary", "reference")
+        if self.boundary not in engine.BOUNDARY_IDS:
+            raise ValueError(f"unknown boundary mode {self.boundary!r} (use 'reference' or 'same')")
+        self.kernel_grid = tuple(self.config.get("kernel_grid", (64, 64, 64)))  # kernel_convolution.py:45
+        self.strict_reference = bool(self.config.get("strict_reference", False))
+        self._plans = engine.PlanCache(capacity=int(self.config.get("plan_cache", 4)))
+        self._kernel_version = 0
+        self._kernel_host: Optional[np.ndarray] = None
+        self._kernel_dev: Optional[torch.Tensor] = None
+        self._aniso_kernels: Dict[tuple, torch.Tensor] = {}
+        self._load_dose_kernel()
+
+    # ------------------------------------------------------------------ kernel state
+    def _load_dose_kernel(self) -> None:
+        self._kernel_dev = self.kernel_factory.get_kernel_device(
+            nuclide=self.radionuclide, tissue_type=self.tissue_name, voxel_size=self.kernel_resolution,
+            grid_size=self.kernel_grid, device=self.device)
+        self._kernel_host = None
+        self._kernel_version += 1
+
+    @property
+    def kernel(self) -> np.ndarray:
+        """Public, assignable kernel (the reference exposes ``self.kernel`` as mutable state)."""
+        if self._kernel_host is None:
+            self._kernel_host = self._kernel_dev.cpu().numpy().astype(np.float64)
+        return self._kernel_host
+
+    @kernel.setter
+    def kernel(self, value) -> None:
+        arr = np.asarray(value)
+        if arr.ndim != 3:
+            raise ValueError("kernel must be a 3-D array")
+        self._kernel_host = arr
+        self._kernel_dev = engine.to_device_f32(arr, self.device)
+        self._kernel_version += 1  # cached spectra are rebuilt on next use
+
+    def _kernel_for(self, voxel_size) -> Tuple[torch.Tensor, object]:
+        if voxel_size is None or _same_spacing(voxel_size, self.kernel_resolution):
+            return self._kernel_dev, ("k", self._kernel_version)
+        if len(tuple(voxel_size)) != 3:
+            raise ValueError("voxel_size must be a tuple of length 3.")
+        if self.strict_reference:
+            raise NotImplementedError(
+                "voxel_size differs from kernel_resolution: the reference's _resample_activity is a stub "
+                "(core/kernel_convolution.py:108-115)")
+        # A10: evaluate the dose voxel kernel on the image grid instead of resampling the activity
+        sp = tuple(float(v) for v in voxel_size)
+        if sp not in self._aniso_kernels:
+            self._aniso_kernels[sp] = self.kernel_factory.get_kernel_device(
+                self.radionuclide, self.tissue_name, sp, self.kernel_grid, device=self.device)
+        return self._aniso_kernels[sp], ("sp", sp)
+
+    # ------------------------------------------------------------------ core
+    def _convolve(self, maps: Sequence, weights: Optional[Sequence[float]], voxel_size, tissue_densities=None,
+                  out: Optional[np.ndarray] = None):
+        if len(maps) == 0:
+            raise ValueError("No activity maps provided")
+        shape = tuple(maps[0].shape)
+        if len(shape) != 3:
+            raise ValueError("activity maps must be 3-D")
+        if any(tuple(m.shape) != shape for m in maps):
+            raise ValueError("All activity maps must have the same dimensions")
+        kdev, tag = self._kernel_for(voxel_size)
+        plan = self._plans.get(shape, tuple(kdev.shape), self.boundary, self.device, tag, lambda: kdev)
+        acts = [engine.to_device_f32(m, self.device) for m in maps]
+        den = None
+        if tissue_densities is not None:
+            den = engine.to_device_f32(tissue_densities, self.device)
+            if tuple(den.shape) != plan.out_shape:
+                raise ValueError("tissue_densities must have the shape of the activity map")
+        cfg = self.config
+        dose = plan.execute(acts, weights, den, float(cfg.get("rho_ref", 1.0)), float(cfg.get("rho_min", 0.1)),
+                            float(cfg.get("rho_cut", 0.0)), float(cfg.get("scale", 1.0)))
+        return dose
+
+    def _to_host(self, dose: torch.Tensor, out=None) -> np.ndarray:
+        want64 = str(self.config.get("output_dtype", "float32")) == "float64"
+        if out is not None:
+            tgt = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
+            tgt.copy_(dose, non_blocking=False)
+            return out if not isinstance(out, torch.Tensor) else out.numpy()
+        host = dose.cpu().numpy()
+        return host.astype(np.float64) if want64 else host
+
+    # ------------------------------------------------------------------ reference API
+    def calculate_dose_rate(self, activity_map, voxel_size: Tuple[float, float, float] = None,
+                            tissue_densities=None, out=None):
+        """A1.  Host ndarray in -> host ndarray out; CUDA tensor in -> CUDA tensor out (no copies)."""
+        dose = self._convolve([activity_map], None, voxel_size, tissue_densities)
+        if isinstance(activity_map, torch.Tensor) and activity_map.is_cuda:
+            return dose
+        return self._to_host(dose, out)
+
+    def calculate_absorbed_dose(self, activity_maps, time_points: List[float], voxel_size=None,
+                                tissue_densities=None, out=None):
+        """A2.  time_points in hours; dose = sum_i w_i * conv(a_i, k), w = trapezoid weights * 3600."""
+        if len(activity_maps) != len(time_points):
+            raise ValueError("Number of activity maps must match number of time points")
+        w = trapezoid_weights(time_points, HOURS_TO_SECONDS)
+        dose = self._convolve(list(activity_maps), w, voxel_size, tissue_densities)
+        if isinstance(activity_maps[0], torch.Tensor) and activity_maps[0].is_cuda:
+            return dose
+        return self._to_host(dose, out)
+
+    def calculate_absorbed_dose_from_accumulated(self, accumulated_activity, voxel_size=None, tissue_densities=None, out=None):
+        """Called by the reference front door (core/dose_calculator.py:104,123) but defined nowhere there;
+        meaning: A1 applied to time-integrated activity (Bq*time -> dose)."""
+        return self.calculate_dose_rate(accumulated_activity, voxel_size, tissue_densities, out)
+
+    def calculate_weighted(self, activity_maps, weights: Sequence[float], voxel_size=None, tissue_densities=None, out=None):
+        """conv(sum_i w_i a_i, k) for caller-chosen weights (used by DoseCalculator's activity mode)."""
+        dose = self._convolve(list(activity_maps), [float(x) for x in weights], voxel_size, tissue_densities)
+        if isinstance(activity_maps[0], torch.Tensor) and activity_maps[0].is_cuda:
+            return dose
+        return self._to_host(dose, out)
+
+    def _resample_activity(self, activity_map, input_voxel_size, output_voxel_size):
+        """The reference stub returns None (kernel_convolution.py:108-115).  Not needed here: the kernel is
+        evaluated on the image grid instead (A10)."""
+        raise NotImplementedError("activity resampling is replaced by evaluating the kernel on the image grid")

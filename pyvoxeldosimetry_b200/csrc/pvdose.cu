@@ -82,10 +82,14 @@ bool is_smooth7(int m) {
     return m == 1;
 }
 
+// Relative cost of an axis of length m: every pass streams the axis through HBM (weight 8) and each
+// radix-r stage costs one shared-memory round trip plus ~log2(r) butterfly levels.
 double size_cost(int m) {
     Stages st;
     if (!make_stages(m, st)) return 1e30;
-    return (double)m * (3.0 + st.n);
+    double c = 8.0;
+    for (int i = 0; i < st.n; ++i) c += 0.3 + 0.35 * std::log2((double)st.radix[i]);
+    return (double)m * c;
 }
 
 int good_size(int n) {
@@ -99,15 +103,9 @@ int good_size(int n) {
             bc = c;
             best = m;
         }
-        if ((double)m * 4.0 > bc) break;  // no later candidate can win
+        if ((double)m * 8.0 > bc) break;  // no later candidate can win
     }
     return best;
-}
-
-int ilog2_floor(int v) {
-    int l = 0;
-    while ((1 << (l + 1)) <= v) ++l;
-    return l;
 }
 
 }  // namespace
@@ -122,6 +120,23 @@ struct pvd_plan {
     size_t off_tw[3], off_buf, off_spec, off_flag, ws_bytes;
     char* ws = nullptr;
     bool kernel_set = false;
+    // measurement hook
+    bool prof = false;
+    bool ev_made = false;
+    cudaEvent_t ev[PVD_MAX_PASSES + 1];
+    int npass = 0;
+    double pass_bytes[PVD_MAX_PASSES];
+    const char* pass_names[PVD_MAX_PASSES];
+    void mark(cudaStream_t s, const char* name, double bytes) {  // call before each launch
+        if (!prof || npass >= PVD_MAX_PASSES) return;
+        cudaEventRecord(ev[npass], s);
+        pass_names[npass] = name;
+        pass_bytes[npass] = bytes;
+        ++npass;
+    }
+    void mark_end(cudaStream_t s) {
+        if (prof) cudaEventRecord(ev[npass], s);
+    }
     float2* tw(int a) const { return reinterpret_cast<float2*>(ws + off_tw[a]); }
     float2* buf() const { return reinterpret_cast<float2*>(ws + off_buf); }
     float2* spec() const { return reinterpret_cast<float2*>(ws + off_spec); }
@@ -374,14 +389,22 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     for (int t = 0; t < T; ++t)
         if (!h_act[t]) return fail(PVD_ERR_INVALID, "activity pointer %d is null", t);
     cudaStream_t stream = (cudaStream_t)stream_;
+    const double c = 8.0 * p->Nh;  // bytes of one half-spectrum row
+    p->npass = 0;
+    p->mark(stream, "P1 rows_fwd (z R2C + time-weighted sum)", 4.0 * T * p->n[0] * p->n[1] * p->n[2] + c * p->n[0] * p->n[1]);
     int rc = launch_rows_fwd(p, h_act, h_weights, T, (long long)p->n[1] * p->n[2], p->n[2], p->n, stream);
     if (rc) return rc;
+    p->mark(stream, "P2 cols y forward", c * p->n[0] * ((double)p->n[1] + p->m[1]));
     rc = launch_cols(p, 1, COL_FWD, p->buf(), p->buf(), 0, p->n[0], p->n[1], 0, p->m[1], 1.f, stream);
     if (rc) return rc;
+    p->mark(stream, "P3 cols x forward*spectrum*inverse", c * p->m[1] * ((double)p->n[0] + p->m[0] + p->on[0]));
     rc = launch_cols(p, 0, COL_CONV, p->buf(), p->buf(), 0, p->m[1], p->n[0], p->olo[0], p->on[0], 1.f, stream);
     if (rc) return rc;
+    p->mark(stream, "P4 cols y inverse", c * p->on[0] * ((double)p->m[1] + p->on[1]));
     rc = launch_cols(p, 1, COL_INV, p->buf(), p->buf(), p->olo[0], p->on[0], p->m[1], p->olo[1], p->on[1], 1.f, stream);
     if (rc) return rc;
+    p->mark(stream, "P5 rows_inv (z C2R + density + crop)",
+            c * p->on[0] * p->on[1] + (density ? 8.0 : 4.0) * p->on[0] * p->on[1] * p->on[2]);
     RowInvArgs a;
     memset(&a, 0, sizeof a);
     a.in = p->buf();
@@ -412,10 +435,40 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     const long long per = 2LL << p->rowLlog;
     PVD_LAUNCH(rows_inv_kernel, dim3((unsigned)((nrows + per - 1) / per)), dim3(PVD_BLOCK), p->rowSmem, stream, a);
     PVD_CUDA_CHECK("rows_inv_kernel");
+    p->mark_end(stream);
     return PVD_OK;
 }
 
+int pvd_plan_set_profiling(pvd_plan* p, int enable) {
+    if (!p) return fail(PVD_ERR_INVALID, "null argument");
+    if (enable && !p->ev_made) {
+        for (int i = 0; i <= PVD_MAX_PASSES; ++i)
+            if (cudaEventCreate(&p->ev[i]) != cudaSuccess) return fail(PVD_ERR_CUDA, "cudaEventCreate failed");
+        p->ev_made = true;
+    }
+    p->prof = enable != 0;
+    p->npass = 0;
+    return PVD_OK;
+}
+
+int pvd_plan_get_pass_times(pvd_plan* p, float* ms, double* hbm_bytes, const char** names, int cap) {
+    if (!p) return fail(PVD_ERR_INVALID, "null argument");
+    if (!p->prof || p->npass == 0) return 0;
+    if (cudaEventSynchronize(p->ev[p->npass]) != cudaSuccess) return fail(PVD_ERR_CUDA, "cudaEventSynchronize failed");
+    const int n = std::min(p->npass, cap);
+    for (int i = 0; i < n; ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, p->ev[i], p->ev[i + 1]);
+        if (ms) ms[i] = t;
+        if (hbm_bytes) hbm_bytes[i] = p->pass_bytes[i];
+        if (names) names[i] = p->pass_names[i];
+    }
+    return n;
+}
+
 int pvd_plan_destroy(pvd_plan* p) {
+    if (p && p->ev_made)
+        for (int i = 0; i <= PVD_MAX_PASSES; ++i) cudaEventDestroy(p->ev[i]);
     delete p;
     return PVD_OK;
 }
@@ -423,40 +476,27 @@ int pvd_plan_destroy(pvd_plan* p) {
 // ---------------------------------------------------------------------------------------------
 static unsigned ew_grid(size_t n) { return (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16); }
 
-int pvd_kernel_eval(int nuclide, const pvd_tissue* t, const float spacing[3], const int g[3], float* out, void* stream) {
-    if (!t || !spacing || !g || !out) return fail(PVD_ERR_INVALID, "null argument");
+int pvd_kernel_eval_radial(const pvd_radial_model* model, const double spacing[3], const int g[3], float* out, void* stream) {
+    if (!model || !spacing || !g || !out) return fail(PVD_ERR_INVALID, "null argument");
     if (g[0] < 1 || g[1] < 1 || g[2] < 1) return fail(PVD_ERR_INVALID, "grid extents must be positive");
+    if (model->n_beta < 0 || model->n_beta > PVD_RADIAL_MAX_TERMS || model->n_photon < 0 || model->n_photon > PVD_RADIAL_MAX_TERMS)
+        return fail(PVD_ERR_INVALID, "at most %d beta and %d photon terms", PVD_RADIAL_MAX_TERMS, PVD_RADIAL_MAX_TERMS);
     RadialModel m;
     memset(&m, 0, sizeof m);
-    const double rho = t->density, S = t->stopping_power_ratio;
-    if (nuclide == PVD_NUCLIDE_Y90) {
-        // data/dose_kernels/y90_kernel.py:93-140, Y90/Y90.json:22
-        m.nb = 1;
-        m.beta_range[0] = 11.0 * std::pow(2.280, 1.5) * (1.0 / rho) * (1.0 / S);
-        m.beta_amp[0] = rho * S;
-        m.np = 1;
-        const double ry = (t->effective_Z / 7.42) * (t->effective_Z / 7.42);
-        m.phot_mu[0] = 0.096 * (rho / 1.0);
-        m.phot_amp[0] = 0.015 * ry * rho;
-    } else if (nuclide == PVD_NUCLIDE_LU177) {
-        // data/dose_kernels/lu177_kernel.py:129-184, Lu177/Lu177.json:21-26
-        const double E[3] = {0.498, 0.385, 0.177}, ab[3] = {0.795, 0.089, 0.116};
-        m.nb = 3;
-        for (int i = 0; i < 3; ++i) {
-            m.beta_range[i] = 5.0 * std::pow(E[i], 1.5) * (1.0 / rho) * (1.0 / S);
-            m.beta_amp[i] = ab[i] * rho * S;
-        }
-        const double Eg[2] = {0.208, 0.113}, Ig[2] = {0.111, 0.062};
-        m.np = 2;
-        for (int i = 0; i < 2; ++i) {
-            m.phot_mu[i] = rho * t->mu_by_rho * std::pow(0.2 / Eg[i], 3.2);
-            m.phot_amp[i] = Ig[i];
-        }
-    } else {
-        return fail(PVD_ERR_INVALID, "unknown nuclide id %d", nuclide);
+    m.nb = model->n_beta;
+    m.np = model->n_photon;
+    for (int i = 0; i < m.nb; ++i) {
+        if (!(model->beta_range[i] > 0.0)) return fail(PVD_ERR_INVALID, "beta range %d must be positive", i);
+        m.beta_range[i] = model->beta_range[i];
+        m.beta_amp[i] = model->beta_amp[i];
     }
-    m.scaling = t->scaling;
+    for (int i = 0; i < m.np; ++i) {
+        m.phot_mu[i] = model->phot_mu[i];
+        m.phot_amp[i] = model->phot_amp[i];
+    }
+    m.scaling = model->scaling;
     for (int i = 0; i < 3; ++i) {
+        if (!(spacing[i] > 0.0)) return fail(PVD_ERR_INVALID, "spacing must be positive");
         m.sp[i] = spacing[i];
         m.g[i] = g[i];
     }

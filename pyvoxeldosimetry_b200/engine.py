@@ -172,16 +172,13 @@ class PlanCache:
 
 
 # ---------------------------------------------------------------------------- elementwise ops
-def kernel_eval(nuclide: str, tissue_props: dict, spacing: Sequence[float], grid: Sequence[int], device=None) -> torch.Tensor:
+def kernel_eval_radial(beta_terms, photon_terms, scaling: float, spacing: Sequence[float], grid: Sequence[int],
+                       device=None) -> torch.Tensor:
+    """Evaluate the radial dose-point-kernel model on the voxel grid, on the device (float32 tensor)."""
     dev = require_cuda(device)
-    lib = get_lib()
-    if nuclide not in _capi.NUCLIDE_IDS:
-        raise ValueError(f"no device generator for {nuclide}")
-    t = _capi.Tissue(tissue_props["density"], tissue_props["effective_Z"], tissue_props["stopping_power_ratio"],
-                     tissue_props.get("mu_by_rho", 0.0), tissue_props.get("scaling", 1.0))
     out = torch.empty(tuple(int(g) for g in grid), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        lib.kernel_eval(_capi.NUCLIDE_IDS[nuclide], t, spacing, grid, out.data_ptr(), _stream_ptr(dev))
+        get_lib().kernel_eval_radial(beta_terms, photon_terms, scaling, spacing, grid, out.data_ptr(), _stream_ptr(dev))
     return out
 
 

@@ -1,0 +1,178 @@
+"""The REAL kernel sources (compiled for the CPU SIMT emulator, see tests/emu_util.py) driven through the
+REAL C ABI against the oracle: index math, radix schedules, crop/pad, fused epilogues, error codes.
+No GPU needed; the numerics bar is the same 1e-4 of peak (observed ~1e-7)."""
+import numpy as np
+import pytest
+
+from emu_util import EmuConv, emu_lib
+from oracle import dose_oracle as orc
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu_lib()
+
+
+def _rand(shape, kshape, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(0, 1e3, shape)
+    a[tuple(s // 2 for s in shape)] = 2e6
+    return a, rng.uniform(0, 1, kshape)
+
+
+CASES = [
+    ((16, 12, 20), (5, 7, 3)), ((10, 9, 8), (12, 4, 11)), ((7, 11, 13), (3, 3, 3)), ((8, 8, 8), (1, 1, 1)),
+    ((12, 10, 14), (4, 6, 2)), ((1, 1, 1), (1, 1, 1)), ((2, 3, 1), (3, 2, 2)), ((25, 9, 27), (3, 3, 3)),
+    ((6, 49, 30), (2, 2, 2)), ((32, 17, 64), (5, 5, 5)), ((5, 34, 38), (3, 3, 3)),
+]
+
+
+@pytest.mark.parametrize("shape,kshape", CASES)
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_conv_vs_oracle(lib, shape, kshape, boundary):
+    a, k = _rand(shape, kshape, hash((shape, kshape)) % 2**32)
+    p = EmuConv(lib, shape, kshape, boundary)
+    p.set_kernel(k)
+    got = p.execute([a])
+    p.close()
+    a32, k32 = a.astype(np.float32).astype(np.float64), k.astype(np.float32).astype(np.float64)
+    ref = orc.conv_reference(a32, k32) if boundary == 0 else orc.conv_same(a32, k32)
+    assert orc.rel_err_of_peak(got, ref) <= TOL
+
+
+def test_time_weights_density_scale(lib):
+    rng = np.random.default_rng(11)
+    shape, kshape = (10, 12, 9), (3, 5, 3)
+    maps = [rng.uniform(0, 1e3, shape) for _ in range(4)]
+    times = [4.0, 24.0, 96.0, 168.0]
+    k = rng.uniform(0, 1, kshape)
+    rho = rng.choice([0.00129, 0.26, 1.04, 1.42], size=shape)
+    w = orc.trapezoid_weights(times, 3600.0)
+    p = EmuConv(lib, shape, kshape, 1)
+    p.set_kernel(k)
+    got = p.execute(maps, [float(x) for x in w], rho, 1.0, 0.1, 0.01, 0.5)
+    p.close()
+    f = lambda x: np.asarray(x, np.float32).astype(np.float64)
+    acc = sum(np.float64(np.float32(wi)) * f(m) for wi, m in zip(w, maps))
+    ref = orc.density_correct(0.5 * orc.conv_same(acc, f(k)), f(rho), 1.0, 0.1, 0.01)
+    assert orc.rel_err_of_peak(got, ref) <= TOL
+    assert np.all(got[rho < 0.01] == 0.0)
+
+
+def test_golden_reference_vectors(lib):
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "conv_ref.npz"))
+    for name in sorted({k.split("|")[0] for k in z.files if k.endswith("|d")}):
+        a, k, d = z[name + "|a"], z[name + "|k"], z[name + "|d"]
+        p = EmuConv(lib, a.shape, k.shape, 0)
+        p.set_kernel(k)
+        got = p.execute([a])
+        p.close()
+        assert orc.rel_err_of_peak(got, d) <= TOL, name
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("boundary", ["reference", "same"])
+def test_slab_plans(lib, world, boundary):
+    """Expert plans (slab + halo in, interior out) stitched over `world` slabs == whole-volume result."""
+    from pyvoxeldosimetry_b200.multi_gpu import slab_geometry
+
+    rng = np.random.default_rng(12)
+    shape, kshape = (13, 6, 10), (4, 3, 5)
+    a, k = rng.uniform(0, 1e3, shape), rng.uniform(0, 1, kshape)
+    f = lambda x: np.asarray(x, np.float32).astype(np.float64)
+    ref = orc.conv_reference(f(a), f(k)) if boundary == "reference" else orc.conv_same(f(a), f(k))
+    out = np.empty(shape, np.float32)
+    for r in range(world):
+        g = slab_geometry(shape, kshape, boundary, world, r, lib)
+        idx = np.arange(g["need_lo"], g["need_hi"])
+        if boundary == "reference":
+            local = a[idx % shape[0]]
+        else:
+            local = np.zeros((len(idx),) + shape[1:])
+            ok = (idx >= 0) & (idx < shape[0])
+            local[ok] = a[idx[ok]]
+        kc = g["kcrop"]
+        p = EmuConv(lib, g["n"], kc, ex=g["ex"])
+        p.set_kernel(k[: kc[0], : kc[1], : kc[2]])
+        out[g["lo"] : g["hi"]] = p.execute([local])
+        p.close()
+    assert orc.rel_err_of_peak(out, ref) <= TOL
+
+
+def test_error_codes(lib):
+    from pyvoxeldosimetry_b200._capi import PvdoseError
+
+    with pytest.raises(PvdoseError) as e:
+        lib.plan_create((0, 4, 4), (3, 3, 3), 0)
+    assert e.value.code == -1
+    with pytest.raises(PvdoseError) as e:
+        lib.plan_create((4, 4, 4), (3, 3, 3), 7)
+    assert e.value.code == -1
+    plan = lib.plan_create((4, 4, 4), (3, 3, 3), 0)
+    x = np.zeros((4, 4, 4), np.float32)
+    with pytest.raises(PvdoseError) as e:  # workspace not set
+        lib.conv_execute(plan, [x.ctypes.data], None, None, 1, 0.1, 0, 1, x.ctypes.data)
+    assert e.value.code == -3
+    lib.plan_destroy(plan)
+    p = EmuConv(lib, (4, 4, 4), (3, 3, 3), 0)
+    with pytest.raises(PvdoseError) as e:  # kernel not set
+        p.execute([x])
+    assert e.value.code == -3
+    k = np.ones((3, 3, 3), np.float32)
+    k[1, 1, 1] = np.nan
+    with pytest.raises(PvdoseError) as e:  # the reference's own Y90 kernel is non-finite: reject loudly
+        p.set_kernel(k)
+    assert e.value.code == -4
+    p.set_kernel(np.ones((3, 3, 3)))
+    with pytest.raises(PvdoseError) as e:
+        lib.conv_execute(p.plan, [x.ctypes.data] * 17, None, None, 1, 0.1, 0, 1, x.ctypes.data)
+    assert e.value.code == -1
+    p.close()
+
+
+def test_good_fft_size(lib):
+    for n in (1, 2, 17, 48, 100, 400, 425, 537, 1000):
+        m = lib.good_fft_size(n)
+        assert m >= n
+        r = m
+        for q in (2, 3, 5, 7):
+            while r % q == 0:
+                r //= q
+        assert r == 1
+
+
+def test_elementwise_ops(lib):
+    rng = np.random.default_rng(13)
+    # radial model == oracle generators (finite centre)
+    from pyvoxeldosimetry_b200.data.dose_kernels.generators import GENERATORS
+
+    for nuc, vox, grid, tissue in (("Y90", 1.0, (9, 8, 7), "bone"), ("Lu177", 4.8, (7, 7, 7), "lung"), ("Y90", (1.0, 2.0, 0.5), (6, 5, 9), "water")):
+        gen = GENERATORS[nuc](tissue)
+        beta, phot, sc = gen.radial_terms()
+        out = np.empty(grid, np.float32)
+        sp = (vox,) * 3 if np.isscalar(vox) else vox
+        lib.kernel_eval_radial(beta, phot, sc, sp, grid, out.ctypes.data)
+        ref = orc.make_kernel(nuc, vox, grid, tissue)
+        np.testing.assert_allclose(out, ref, rtol=2e-7, atol=0)
+    hu = rng.uniform(-1200, 3500, 1000).astype(np.float32)
+    rho = np.empty_like(hu)
+    lib.hu_to_density(hu.ctypes.data, False, orc.HU_KNOTS.tolist(), rho.ctypes.data, hu.size)
+    np.testing.assert_allclose(rho, orc.hu_to_density(hu), rtol=2e-6)
+    hi = rng.integers(-1100, 3200, 1000).astype(np.int16)
+    lib.hu_to_density(hi.ctypes.data, True, orc.HU_KNOTS.tolist(), rho.ctypes.data, hi.size)
+    np.testing.assert_allclose(rho, orc.hu_to_density(hi), rtol=2e-6)
+    vols = [rng.uniform(0, 1, 777).astype(np.float32) for _ in range(5)]
+    w = [0.5, 1.0, 2.0, -1.0, 3.0]
+    out = np.empty(777, np.float32)
+    lib.weighted_sum([v.ctypes.data for v in vols], w, out.ctypes.data, 777)
+    np.testing.assert_allclose(out, sum(wi * v.astype(np.float64) for wi, v in zip(w, vols)), rtol=1e-6)
+    a0, lam = rng.uniform(0, 1e4, 500).astype(np.float32), rng.uniform(1e-3, 1e-1, 500).astype(np.float32)
+    lib.monoexp_integral(a0.ctypes.data, lam.ctypes.data, 72.0, out.ctypes.data, 500)
+    np.testing.assert_allclose(out[:500], orc.accumulated_activity_monoexp(a0, lam, 161.52, 72.0), rtol=2e-6)
+    d, r = rng.uniform(0, 1, 300).astype(np.float32), rng.uniform(0, 2, 300).astype(np.float32)
+    lib.density_scale(d.ctypes.data, r.ctypes.data, 1.0, 0.1, 0.05, 2.0, out.ctypes.data, 300)
+    np.testing.assert_allclose(out[:300], orc.density_correct(2.0 * d.astype(np.float64), r, 1.0, 0.1, 0.05), rtol=1e-6)

@@ -74,7 +74,12 @@ class DoseCalculator:
                 # integrate activity (caller's time unit, activity_sampler.py:74-78), then one convolution
                 w = trapezoid_weights(time_points, 1.0)
                 dose = calc.calculate_weighted(maps, w, voxel_size, tissue_densities)
-                return DoseCalculationResult(dose, [], time_points, {"mode": "multi_timepoint_activity"})
+                rates = []
+                if not calc.strict_reference and self.config.get("return_dose_rate_maps", True):
+                    # the reference returns [] here yet its own example plots result.dose_rate_maps[i]
+                    # (examples/time_integrated_dose.py:110); on the GPU the T extra convolutions are cheap
+                    rates = [calc.calculate_dose_rate(a, voxel_size, tissue_densities) for a in maps]
+                return DoseCalculationResult(dose, rates, time_points, {"mode": "multi_timepoint_activity"})
             if integration_mode == "dose_rate":
                 rates = [calc.calculate_dose_rate(a, voxel_size, tissue_densities) for a in maps]
                 dose = self.activity_sampler.integrate_dose_rates(rates, time_points, integration_limit)

@@ -1,0 +1,295 @@
+// Size-specialised ("fast") versions of the five passes.
+//
+// Same mathematics and argument structs as fft_passes.cuh, but everything about the transform is a
+// compile-time constant: length N, radix schedule (R1,R2[,R3]), tile width W = 16 lines (one 128-byte
+// line of float2 per transform index) and the thread count NT.  Consequences:
+//   * every radix stage runs in registers; the first stage of a column pass loads straight from HBM
+//     (each half-warp reads one full 128-byte line), the last stage stores straight back - shared
+//     memory is only the exchange buffer between stages (ONE buffer, N*16*8 bytes, in place);
+//   * in the x pass the forward transform ends and the inverse transform starts in the same registers:
+//     forward -> multiply by the cached kernel spectrum -> inverse without touching memory;
+//   * all index arithmetic folds to shifts/immediates, inter-stage twiddles come from a shared-memory
+//     copy of the N-th roots table.
+// Sizes outside the instantiated menu fall back to the generic engine in fft_passes.cuh.
+#pragma once
+#include "fft_passes.cuh"
+
+namespace pvd {
+
+// One Stockham DIF stage with radix R and stride S.  in(u, j, idx, w) -> float2, out(u, k, idx, w, v).
+// (u, j)/(u, k) are the register slots (compile-time after unrolling), idx the transform index, w the line.
+template <int N, int W, int NT, int R, int S, int DIR, bool SYNC_AFTER_READ, class In, class Out>
+__device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __restrict__ tws) {
+    constexpr int NB = N / R;          // butterflies per line
+    constexpr int M = NB / S;
+    constexpr int TPC = NT / W;        // butterflies of one line processed concurrently
+    constexpr int BPT = (NB + TPC - 1) / TPC;
+    constexpr bool GUARD = (NB % TPC) != 0;
+    static_assert(N % R == 0 && NB % S == 0 && NT % W == 0, "bad radix schedule");
+    const int w = threadIdx.x % W;
+    const int b0 = threadIdx.x / W;
+    float2 a[BPT][R];
+    PVD_UNROLL
+    for (int u = 0; u < BPT; ++u) {
+        const int b = b0 + u * TPC;
+        if (!GUARD || b < NB) {
+            const int p = b / S, q = b % S;
+            PVD_UNROLL
+            for (int j = 0; j < R; ++j) a[u][j] = in(u, j, q + S * (p + M * j), w);
+        }
+    }
+    if (SYNC_AFTER_READ) __syncthreads();
+    PVD_UNROLL
+    for (int u = 0; u < BPT; ++u) {
+        const int b = b0 + u * TPC;
+        if (!GUARD || b < NB) {
+            const int p = b / S, q = b % S;
+            Dft<R, DIR>::run(a[u]);
+            if (M > 1) {
+                PVD_UNROLL
+                for (int k = 1; k < R; ++k) {
+                    float2 t = tws[p * S * k];
+                    if (DIR > 0) t.y = -t.y;
+                    a[u][k] = cmul(a[u][k], t);
+                }
+            }
+            PVD_UNROLL
+            for (int k = 0; k < R; ++k) out(u, k, q + S * (R * p + k), w, a[u][k]);
+        }
+    }
+}
+
+// Whole transform.  Stage list (R1, R2, R3) with R3 == 1 meaning two stages.  IN_SMEM / OUT_SMEM say
+// whether `in` / `out` address the exchange tile itself (then reads must complete before writes).
+template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out>
+__device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws) {
+    static_assert(R1 * R2 * R3 == N, "radix schedule must multiply to N");
+    auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
+    auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
+    fast_stage<N, W, NT, R1, 1, DIR, IN_SMEM>(in, sm_out, tws);
+    __syncthreads();
+    if constexpr (R3 > 1) {
+        fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws);
+        __syncthreads();
+        fast_stage<N, W, NT, R3, R1 * R2, DIR, OUT_SMEM>(sm_in, out, tws);
+    } else {
+        fast_stage<N, W, NT, R2, R1, DIR, OUT_SMEM>(sm_in, out, tws);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column passes (axis 1 forward / inverse, axis 0 forward * spectrum * inverse, kernel spectrum).
+template <int N, int NT, int R1, int R2, int R3, int MODE>
+__global__ void __launch_bounds__(NT) cols_fast_kernel(const ColArgs g) {
+    constexpr int W = 16;
+    constexpr int RL = (R3 > 1) ? R3 : R2;  // radix of the last forward stage
+    constexpr int TPC = NT / W;
+    constexpr int BPTL = (N / RL + TPC - 1) / TPC;
+    PVD_DYN_SMEM(float2, smem);
+    float2* tile = smem;
+    float2* tws = smem + N * W;
+    for (int i = threadIdx.x; i < N; i += NT) tws[i] = g.tw[i];
+    const int z0 = blockIdx.x * W;
+    const long long base = (long long)(g.outer0 + (int)blockIdx.y) * g.os + z0;
+    const int zlim = g.nzf - z0;
+    const float2* __restrict__ src = g.in + base;
+    float2* __restrict__ dst = g.out + base;
+    const long long es = g.es;
+    const int n_in = g.n_in, lo = g.out_lo, hi = g.out_lo + g.out_n;
+    auto gin = [&](int, int, int r, int w) -> float2 {
+        return (r < n_in && w < zlim) ? src[(long long)r * es + w] : make_float2(0.f, 0.f);
+    };
+    __syncthreads();  // twiddle table visible
+    if constexpr (MODE == COL_FWD || MODE == COL_SPEC) {
+        const float sc = g.scale;
+        auto gout = [&](int, int, int r, int w, float2 v) {
+            if (MODE == COL_SPEC) v = make_float2(v.x * sc, v.y * sc);
+            if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = v;
+        };
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, gout, tile, tws);
+    } else if constexpr (MODE == COL_INV) {
+        auto gout = [&](int, int, int r, int w, float2 v) {
+            if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = v;
+        };
+        fast_fft<N, W, W, NT, +1, R1, R2, R3, false, false>(gin, gout, tile, tws);
+    } else {  // COL_CONV: forward -> * spectrum -> inverse, the middle never leaves registers
+        float2 hold[BPTL][RL];
+        auto rout = [&](int u, int k, int, int, float2 v) { hold[u][k] = v; };
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, rout, tile, tws);
+        const float2* __restrict__ sp = g.spec + base;
+        const int wl = threadIdx.x % W, b0 = threadIdx.x / W;
+        PVD_UNROLL
+        for (int u = 0; u < BPTL; ++u) {
+            const int b = b0 + u * TPC;
+            if (b < N / RL) {
+                PVD_UNROLL
+                for (int k = 0; k < RL; ++k) {
+                    const int r = b + (N / RL) * k;
+                    if (wl < zlim) hold[u][k] = cmul(hold[u][k], __ldg(&sp[(long long)r * es + wl]));
+                }
+            }
+        }
+        __syncthreads();  // every thread finished reading the tile in the last forward stage
+        auto rin = [&](int u, int j, int, int) -> float2 { return hold[u][j]; };
+        auto gout = [&](int, int, int r, int w, float2 v) {
+            if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = v;
+        };
+        if constexpr (R3 > 1)
+            fast_fft<N, W, W, NT, +1, R3, R2, R1, false, false>(rin, gout, tile, tws);
+        else
+            fast_fft<N, W, W, NT, +1, R2, R1, 1, false, false>(rin, gout, tile, tws);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row passes: 32 real rows = 16 packed complex lines per block; tile stride 17 keeps the transposing
+// loads/stores at 2-way bank conflicts and the butterflies conflict-free.
+template <int N, int NT, int R1, int R2, int R3>
+__global__ void __launch_bounds__(NT) rows_fwd_fast_kernel(const RowFwdArgs g) {
+    constexpr int W = 16, LS = 17;
+    PVD_DYN_SMEM(float2, smem);
+    float2* tile = smem;
+    float2* tws = smem + N * LS;
+    for (int i = threadIdx.x; i < N; i += NT) tws[i] = g.tw[i];
+    const long long nrows = (long long)g.n0 * g.n1;
+    const long long row0 = (long long)blockIdx.x * (2 * W);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NWARPS = NT / 32;
+    float* Af = reinterpret_cast<float*>(tile);
+    const int T = g.T, n2 = g.n2;
+    for (int rr = warp; rr < 2 * W; rr += NWARPS) {
+        const long long R = row0 + rr;
+        const bool valid = R < nrows;
+        long long off = 0;
+        if (valid) {
+            const long long x = R / g.n1, y = R - x * g.n1;
+            off = x * g.in_s0 + y * g.in_s1;
+        }
+        float* dstf = Af + (rr >> 1) * 2 + (rr & 1);
+        if (T == 1) {
+            const float* __restrict__ p0 = g.in[0] + off;
+            const float w0 = g.w[0];
+            PVD_UNROLL
+            for (int z = lane; z < N; z += 32) dstf[z * (2 * LS)] = (valid && z < n2) ? w0 * __ldg(p0 + z) : 0.f;
+        } else {
+            for (int z = lane; z < N; z += 32) {
+                float v = 0.f;
+                if (valid && z < n2)
+                    for (int t = 0; t < T; ++t) v += g.w[t] * __ldg(g.in[t] + off + z);
+                dstf[z * (2 * LS)] = v;
+            }
+        }
+    }
+    __syncthreads();
+    auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
+    auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
+    fast_fft<N, W, LS, NT, -1, R1, R2, R3, true, true>(sm_in, sm_out, tile, tws);
+    __syncthreads();
+    const int Nh = g.Nh;
+    for (int rr = warp; rr < 2 * W; rr += NWARPS) {
+        const long long R = row0 + rr;
+        if (R >= nrows) continue;
+        const long long x = R / g.n1, y = R - x * g.n1;
+        float2* __restrict__ dst = g.out + x * g.out_s0 + y * g.out_s1;
+        const int line = rr >> 1;
+        const bool odd = rr & 1;
+        for (int k = lane; k < Nh; k += 32) {
+            const float2 zk = tile[k * LS + line];
+            const float2 zm = tile[((k == 0) ? 0 : N - k) * LS + line];
+            dst[k] = odd ? make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x))
+                         : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        }
+    }
+}
+
+template <int N, int NT, int R1, int R2, int R3>
+__global__ void __launch_bounds__(NT) rows_inv_fast_kernel(const RowInvArgs g) {
+    constexpr int W = 16, LS = 17;
+    PVD_DYN_SMEM(float2, smem);
+    float2* tile = smem;
+    float2* tws = smem + N * LS;
+    for (int i = threadIdx.x; i < N; i += NT) tws[i] = g.tw[i];
+    const long long nrows = (long long)g.O0 * g.O1;
+    const long long row0 = (long long)blockIdx.x * (2 * W);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NWARPS = NT / 32;
+    const int Nh = g.Nh;
+    for (int line = warp; line < W; line += NWARPS) {
+        const long long Ra = row0 + 2 * line, Rb = Ra + 1;
+        const bool va = Ra < nrows, vb = Rb < nrows;
+        const float2 *pa = g.in, *pb = g.in;
+        if (va) {
+            const long long xa = Ra / g.O1, ya = Ra - xa * g.O1;
+            pa = g.in + (xa + g.x_lo) * g.in_s0 + (ya + g.y_lo) * g.in_s1;
+        }
+        if (vb) {
+            const long long xb = Rb / g.O1, yb = Rb - xb * g.O1;
+            pb = g.in + (xb + g.x_lo) * g.in_s0 + (yb + g.y_lo) * g.in_s1;
+        }
+        // all global loads of the line first (memory-level parallelism), then the packing
+        constexpr int KIT = (N / 2 + 1 + 31) / 32;
+        float2 av[KIT], bv[KIT];
+        PVD_UNROLL
+        for (int i = 0; i < KIT; ++i) {
+            const int k = lane + 32 * i;
+            av[i] = (va && k < Nh) ? pa[k] : make_float2(0.f, 0.f);
+            bv[i] = (vb && k < Nh) ? pb[k] : make_float2(0.f, 0.f);
+        }
+        PVD_UNROLL
+        for (int i = 0; i < KIT; ++i) {
+            const int k = lane + 32 * i;
+            if (k < Nh) {
+                float2 a = av[i], b = bv[i];
+                const int mk = N - k;
+                const bool self = (k == 0) || (mk == k);
+                if (self) {
+                    a.y = 0.f;
+                    b.y = 0.f;
+                }
+                tile[k * LS + line] = make_float2(a.x - b.y, a.y + b.x);
+                if (!self) tile[mk * LS + line] = make_float2(a.x + b.y, b.x - a.y);
+            }
+        }
+    }
+    __syncthreads();
+    auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
+    auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
+    fast_fft<N, W, LS, NT, +1, R1, R2, R3, true, true>(sm_in, sm_out, tile, tws);
+    __syncthreads();
+    const float* Zf = reinterpret_cast<const float*>(tile);
+    const float scale = g.scale, rho_ref = g.rho_ref, rho_min = g.rho_min, rho_cut = g.rho_cut;
+    const int O2 = g.O2, z_lo = g.z_lo;
+    for (int rr = warp; rr < 2 * W; rr += NWARPS) {
+        const long long R = row0 + rr;
+        if (R >= nrows) continue;
+        const long long x = R / g.O1, y = R - x * g.O1;
+        float* __restrict__ dst = g.out + x * g.out_s0 + y * g.out_s1;
+        const float* srcf = Zf + (rr >> 1) * 2 + (rr & 1) + (size_t)z_lo * (2 * LS);
+        constexpr int ZIT = (N + 31) / 32;
+        if (g.density) {
+            const float* __restrict__ den = g.density + x * g.den_s0 + y * g.den_s1;
+            float rho[ZIT];
+            PVD_UNROLL
+            for (int i = 0; i < ZIT; ++i) {
+                const int z = lane + 32 * i;
+                rho[i] = (z < O2) ? __ldg(den + z) : 1.f;
+            }
+            PVD_UNROLL
+            for (int i = 0; i < ZIT; ++i) {
+                const int z = lane + 32 * i;
+                if (z < O2) {
+                    const float v = srcf[z * (2 * LS)] * scale;
+                    dst[z] = (rho[i] < rho_cut) ? 0.f : v * __fdividef(rho_ref, fmaxf(rho[i], rho_min));
+                }
+            }
+        } else {
+            PVD_UNROLL
+            for (int i = 0; i < ZIT; ++i) {
+                const int z = lane + 32 * i;
+                if (z < O2) dst[z] = srcf[z * (2 * LS)] * scale;
+            }
+        }
+    }
+}
+
+}  // namespace pvd

@@ -1,0 +1,133 @@
+// Persistent, software-pipelined column passes.
+//
+// One CTA per SM walks a strided list of column tiles (N transform indices x 16 frequencies = N full
+// 128-byte lines).  While the FFT of tile i runs out of shared-memory buffer i&1, the HBM loads of tile
+// i+1 are already in flight into the other buffer (cp.async.cg 16-byte copies, no registers held, zero
+// fill for the padded rows); results leave straight from registers (fire-and-forget stores).  In the
+// x pass the matching tile of the cached kernel spectrum is prefetched into registers at the start of the
+// tile and consumed after the forward transform.  The point is memory-level parallelism: ncu showed the
+// non-pipelined kernels stalled on long_scoreboard with ~50 % issue activity (profiles/r01_ncu_fast.md).
+#pragma once
+#include "fft_fast.cuh"
+
+namespace pvd {
+
+#ifdef PVD_EMULATE
+static inline void cp_async16(void* dst, const void* src, bool valid) {
+    if (valid) std::memcpy(dst, src, 16);
+    else std::memset(dst, 0, 16);
+}
+static inline void cp_async_commit() {}
+template <int K> static inline void cp_async_wait() {}
+#else
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros, nothing read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
+#endif
+
+struct ColPipeArgs {
+    ColArgs c;
+    int ntz;     // tiles along the frequency axis
+    int ntiles;  // ntz * number of outer indices
+};
+
+template <int N, int NT, int MINB, int R1, int R2, int R3, int MODE>
+__global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const ColPipeArgs pa) {
+    constexpr int W = 16;
+    constexpr int RL = (R3 > 1) ? R3 : R2;
+    constexpr int TPC = NT / W;
+    constexpr int BPTL = (N / RL + TPC - 1) / TPC;
+    constexpr int CHUNKS = N * 8;  // 16-byte chunks per tile
+    static_assert(CHUNKS % NT == 0 && NT % 8 == 0, "tile must split evenly over the threads");
+    const ColArgs& g = pa.c;
+    PVD_DYN_SMEM(float2, smem);
+    float2* tws = smem + 2 * N * W;
+    for (int i = threadIdx.x; i < N; i += NT) tws[i] = g.tw[i];
+    const long long es = g.es;
+    const int n_in = g.n_in, lo = g.out_lo, hi = g.out_lo + g.out_n;
+    const int ntz = pa.ntz, ntiles = pa.ntiles;
+    const int crow = threadIdx.x >> 3, ccol = (threadIdx.x & 7) * 2;  // this thread's chunk inside a row group
+    auto tile_base = [&](int t) -> long long {
+        const int zt = t % ntz, outer = t / ntz;
+        return (long long)(g.outer0 + outer) * g.os + (long long)zt * W;
+    };
+    auto issue = [&](float2* buf, int t) {
+        const float2* src = g.in + tile_base(t) + (long long)crow * es + ccol;
+        float2* dstp = buf + crow * W + ccol;
+        PVD_UNROLL
+        for (int i = 0; i < CHUNKS / NT; ++i) {
+            const int r = crow + i * (NT / 8);
+            cp_async16(dstp, src, r < n_in);
+            src += (long long)(NT / 8) * es;
+            dstp += (NT / 8) * W;
+        }
+    };
+    int t = blockIdx.x;
+    if (t < ntiles) issue(smem, t);
+    cp_async_commit();
+    int cur = 0;
+    const int wl = threadIdx.x % W, b0 = threadIdx.x / W;
+    for (; t < ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) issue(smem + (cur ^ 1) * (N * W), tn);
+        cp_async_commit();
+        const long long base = tile_base(t);
+        const int zlim = g.nzf - (t % ntz) * W;
+        float2* __restrict__ dst = g.out + base;
+        float2 sp[BPTL][RL];
+        if constexpr (MODE == COL_CONV) {  // spectrum tile -> registers, consumed after the forward transform
+            const float2* __restrict__ spp = g.spec + base;
+            PVD_UNROLL
+            for (int u = 0; u < BPTL; ++u) {
+                const int b = b0 + u * TPC;
+                PVD_UNROLL
+                for (int k = 0; k < RL; ++k) {
+                    const int r = b + (N / RL) * k;
+                    sp[u][k] = (b < N / RL && wl < zlim) ? __ldg(&spp[(long long)r * es + wl]) : make_float2(0.f, 0.f);
+                }
+            }
+        }
+        cp_async_wait<1>();  // everything but the prefetch just issued has landed
+        __syncthreads();
+        float2* tile = smem + cur * (N * W);
+        auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * W + w]; };
+        auto gout = [&](int, int, int r, int w, float2 v) {
+            if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = v;
+        };
+        if constexpr (MODE == COL_FWD) {
+            fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(sm_in, gout, tile, tws);
+        } else if constexpr (MODE == COL_SPEC) {
+            const float sc = g.scale;
+            auto sout = [&](int, int, int r, int w, float2 v) {
+                if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = make_float2(v.x * sc, v.y * sc);
+            };
+            fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(sm_in, sout, tile, tws);
+        } else if constexpr (MODE == COL_INV) {
+            fast_fft<N, W, W, NT, +1, R1, R2, R3, true, false>(sm_in, gout, tile, tws);
+        } else {
+            float2 hold[BPTL][RL];
+            auto rout = [&](int u, int k, int, int, float2 v) { hold[u][k] = v; };
+            fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(sm_in, rout, tile, tws);
+            PVD_UNROLL
+            for (int u = 0; u < BPTL; ++u) {
+                PVD_UNROLL
+                for (int k = 0; k < RL; ++k) hold[u][k] = cmul(hold[u][k], sp[u][k]);
+            }
+            __syncthreads();  // all reads of the tile by the last forward stage are done
+            auto rin = [&](int u, int j, int, int) -> float2 { return hold[u][j]; };
+            if constexpr (R3 > 1)
+                fast_fft<N, W, W, NT, +1, R3, R2, R1, false, false>(rin, gout, tile, tws);
+            else
+                fast_fft<N, W, W, NT, +1, R2, R1, 1, false, false>(rin, gout, tile, tws);
+        }
+        __syncthreads();  // tile buffer may be refilled by the next iteration's prefetch
+        cur ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace pvd

@@ -68,6 +68,10 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 3; return 0; }  // 3 "SMs": tiles > CTAs in tests
+template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 1; return 0; }
 typedef void* cudaEvent_t;
 static inline cudaError_t cudaEventCreate(cudaEvent_t*) { return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }

@@ -8,6 +8,8 @@
 #include <vector>
 
 #include "elementwise.cuh"
+#include "fft_fast.cuh"
+#include "fft_pipe.cuh"
 #include "fft_passes.cuh"
 
 using namespace pvd;
@@ -108,6 +110,57 @@ int good_size(int n) {
     return best;
 }
 
+// ---- size-specialised kernel menu (fft_fast.cuh) ------------------------------------------------
+typedef void (*ColKernelFn)(const ColArgs);
+typedef void (*RowFwdKernelFn)(const RowFwdArgs);
+typedef void (*RowInvKernelFn)(const RowInvArgs);
+typedef void (*ColPipeKernelFn)(const ColPipeArgs);
+struct FastCols {
+    int N, NT;
+    ColKernelFn fn[4];        // one tile per CTA, indexed by ColMode
+    ColPipeKernelFn pipe[4];  // persistent cp.async-pipelined variant (null when the double buffer does not fit)
+};
+struct FastRows {
+    int N, NT;
+    RowFwdKernelFn fwd;
+    RowInvKernelFn inv;
+};
+#define PVD_COLS_FN(N, NT, R1, R2, R3)                                                             \
+    {                                                                                                  \
+        cols_fast_kernel<N, NT, R1, R2, R3, COL_FWD>, cols_fast_kernel<N, NT, R1, R2, R3, COL_INV>,    \
+            cols_fast_kernel<N, NT, R1, R2, R3, COL_CONV>, cols_fast_kernel<N, NT, R1, R2, R3, COL_SPEC> \
+    }
+#define PVD_COLS_PIPE(N, NT, MINB, R1, R2, R3)                                                                     \
+    {                                                                                                              \
+        cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_FWD>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_INV>,    \
+            cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_CONV>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC> \
+    }
+#define PVD_COLS(N, NT, MINB, R1, R2, R3) { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), PVD_COLS_PIPE(N, NT, MINB, R1, R2, R3) }
+#define PVD_COLS_NOPIPE(N, NT, R1, R2, R3) { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), {nullptr, nullptr, nullptr, nullptr} }
+#define PVD_ROWS(N, NT, R1, R2, R3) \
+    { N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3> }
+const FastCols kFastCols[] = {
+    PVD_COLS(512, 512, 1, 8, 8, 8),
+    PVD_COLS(256, 256, 2, 16, 16, 1),
+    PVD_COLS(400, 320, 1, 20, 20, 1),
+    PVD_COLS_NOPIPE(1024, 1024, 16, 8, 8),
+};
+const FastRows kFastRows[] = {
+    PVD_ROWS(400, 320, 20, 20, 1),
+    PVD_ROWS(256, 256, 16, 16, 1),
+    PVD_ROWS(512, 512, 8, 8, 8),
+};
+const FastCols* find_fast_cols(int n) {
+    for (const auto& e : kFastCols)
+        if (e.N == n) return &e;
+    return nullptr;
+}
+const FastRows* find_fast_rows(int n) {
+    for (const auto& e : kFastRows)
+        if (e.N == n) return &e;
+    return nullptr;
+}
+
 }  // namespace
 
 struct pvd_plan {
@@ -115,8 +168,12 @@ struct pvd_plan {
     int Nh, Sz;
     int algo;
     Stages st[3];
-    int rowLlog, colWlog[2];          // tile shapes
+    int rowLlog, colWlog[2];          // tile shapes (generic engine)
     size_t rowSmem, colSmem[2];
+    const FastCols* fastCols[2] = {nullptr, nullptr};  // size-specialised kernels, when the length is on the menu
+    const FastRows* fastRows = nullptr;
+    bool usePipe = true;
+    int pipeGrid[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // persistent grid size per axis / mode
     size_t off_tw[3], off_buf, off_spec, off_flag, ws_bytes;
     char* ws = nullptr;
     bool kernel_set = false;
@@ -171,6 +228,13 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
     const long long per = 2LL << p->rowLlog;
     const long long nblk = (nrows + per - 1) / per;
     if (nblk <= 0) return PVD_OK;
+    if (p->fastRows) {
+        const FastRows* f = p->fastRows;
+        const size_t smem = ((size_t)f->N * 17 + f->N) * sizeof(float2);
+        PVD_LAUNCH(f->fwd, dim3((unsigned)((nrows + 31) / 32)), dim3(f->NT), smem, stream, a);
+        PVD_CUDA_CHECK("rows_fwd_fast_kernel");
+        return PVD_OK;
+    }
     PVD_LAUNCH(rows_fwd_kernel, dim3((unsigned)nblk), dim3(PVD_BLOCK), p->rowSmem, stream, a);
     PVD_CUDA_CHECK("rows_fwd_kernel");
     return PVD_OK;
@@ -199,6 +263,25 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
     a.st = p->st[axis];
     const int W = 1 << a.Wlog;
     if (nouter <= 0) return PVD_OK;
+    if (p->fastCols[axis] && p->fastCols[axis]->pipe[mode] && p->usePipe && p->pipeGrid[axis][mode] > 0) {
+        const FastCols* f = p->fastCols[axis];
+        ColPipeArgs pa;
+        pa.c = a;
+        pa.ntz = (p->Nh + 15) / 16;
+        pa.ntiles = pa.ntz * nouter;
+        const size_t smem = ((size_t)f->N * 32 + f->N) * sizeof(float2);
+        const int grid = std::min(pa.ntiles, p->pipeGrid[axis][mode]);
+        PVD_LAUNCH(f->pipe[mode], dim3((unsigned)grid), dim3(f->NT), smem, stream, pa);
+        PVD_CUDA_CHECK("cols_pipe_kernel");
+        return PVD_OK;
+    }
+    if (p->fastCols[axis]) {
+        const FastCols* f = p->fastCols[axis];
+        const size_t smem = ((size_t)f->N * 16 + f->N) * sizeof(float2);
+        PVD_LAUNCH(f->fn[mode], dim3((unsigned)((p->Nh + 15) / 16), (unsigned)nouter), dim3(f->NT), smem, stream, a);
+        PVD_CUDA_CHECK("cols_fast_kernel");
+        return PVD_OK;
+    }
     PVD_LAUNCH(cols_kernel, dim3((unsigned)((p->Nh + W - 1) / W), (unsigned)nouter), dim3(PVD_BLOCK), p->colSmem[axis],
                stream, a);
     PVD_CUDA_CHECK("cols_kernel");
@@ -249,6 +332,13 @@ int plan_finish(pvd_plan* p) {
     off = align_up(off + 256, 256);
     p->ws_bytes = off;
     p->algo = PVD_ALGO_FFT;
+    const char* force = getenv("PVD_FORCE_GENERIC");
+    if (!(force && force[0] == '1')) {
+        for (int a = 0; a < 2; ++a) p->fastCols[a] = find_fast_cols(p->m[a]);
+        p->fastRows = find_fast_rows(p->m[2]);
+    }
+    const char* nopipe = getenv("PVD_NO_PIPE");
+    p->usePipe = !(nopipe && nopipe[0] == '1');
     return PVD_OK;
 }
 
@@ -343,6 +433,23 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
                    p->m[a]);
         PVD_CUDA_CHECK("twiddle_kernel");
     }
+    for (int a = 0; a < 2; ++a)
+        if (p->fastCols[a])
+            for (int md = 0; md < 4; ++md)
+            {
+                const FastCols* f = p->fastCols[a];
+                if (PVD_SET_SMEM(f->fn[md], kMaxSmem) != 0) return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (cols)");
+                if (f->pipe[md]) {
+                    if (PVD_SET_SMEM(f->pipe[md], kMaxSmem) != 0) return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (pipe)");
+                    int dev = 0, sms = 0, per = 0;
+                    cudaGetDevice(&dev);
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->pipe[md], f->NT, ((size_t)f->N * 32 + f->N) * sizeof(float2));
+                    p->pipeGrid[a][md] = sms * per;  // one resident wave: every CTA stays on its SM and loops
+                }
+            }
+    if (p->fastRows && (PVD_SET_SMEM(p->fastRows->fwd, kMaxSmem) != 0 || PVD_SET_SMEM(p->fastRows->inv, kMaxSmem) != 0))
+        return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (rows)");
     if (PVD_SET_SMEM(rows_fwd_kernel, kMaxSmem) != 0 || PVD_SET_SMEM(rows_inv_kernel, kMaxSmem) != 0 ||
         PVD_SET_SMEM(cols_kernel, kMaxSmem) != 0) {
         cudaGetLastError();
@@ -433,6 +540,14 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     a.st = p->st[2];
     const long long nrows = (long long)p->on[0] * p->on[1];
     const long long per = 2LL << p->rowLlog;
+    if (p->fastRows) {
+        const FastRows* f = p->fastRows;
+        const size_t smem = ((size_t)f->N * 17 + f->N) * sizeof(float2);
+        PVD_LAUNCH(f->inv, dim3((unsigned)((nrows + 31) / 32)), dim3(f->NT), smem, stream, a);
+        PVD_CUDA_CHECK("rows_inv_fast_kernel");
+        p->mark_end(stream);
+        return PVD_OK;
+    }
     PVD_LAUNCH(rows_inv_kernel, dim3((unsigned)((nrows + per - 1) / per)), dim3(PVD_BLOCK), p->rowSmem, stream, a);
     PVD_CUDA_CHECK("rows_inv_kernel");
     p->mark_end(stream);

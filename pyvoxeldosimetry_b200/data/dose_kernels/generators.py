@@ -124,4 +124,18 @@ class Ga68KernelGenerator(BaseKernelGenerator):
         return beta, phot, f
 
 
-GENERATORS: Dict[str, type] = {"Y90": Y90KernelGenerator, "Lu177": Lu177KernelGenerator, "Ga68": Ga68KernelGenerator}
+class F18KernelGenerator(Ga68KernelGenerator):
+    """F-18: positron range + 511 keV annihilation photons.  The reference's generator cannot run
+    (_calculate_beta_range / _dose_point_value are `pass`, f18_kernel.py:38-46; its docstring states the
+    intent: "positron range and annihilation photon contributions"), so this uses the positron form of the
+    Ga68 generator with E_max = 0.634 MeV (F18/F18.json:22).  PARITY UNPINNED - no reference values exist."""
+    nuclide = "F18"
+
+    def __init__(self, tissue_type: str):
+        BaseKernelGenerator.__init__(self, tissue_type)
+        n = NUCLIDES["F18"]
+        self.beta_max_energy, self.gamma_lines = n["beta_max"], n["gamma_lines"]
+
+
+GENERATORS: Dict[str, type] = {"Y90": Y90KernelGenerator, "Lu177": Lu177KernelGenerator, "Ga68": Ga68KernelGenerator,
+                               "F18": F18KernelGenerator}

@@ -2,7 +2,7 @@
 
 Values restate the reference's data files (citations per entry); they are data, not code:
   Y90   data/dose_kernels/Y90/Y90.json:16,22-24      Lu177 data/dose_kernels/Lu177/Lu177.json:16,21-26
-  Ga68  data/dose_kernels/Ga68/Ga68.json:16,22-27
+  Ga68  data/dose_kernels/Ga68/Ga68.json:16,22-27   F18 data/dose_kernels/F18/F18.json:16,22-24
 Tissue tables: data/dose_kernels/y90_kernel.py:59-90, lu177_kernel.py:90-126, ga68_kernel.py:85-106.
 The reference's Lu177/Ga68 JSON files carry `//` comments and cannot be parsed by json.load
 (SURVEY.md Appendix B2), which is why the constants live in Python here.
@@ -15,13 +15,16 @@ NUCLIDES = {
     "Lu177": {"name": "Lutetium-177", "symbol": "Lu177", "half_life": 161.52, "beta_max": (0.498, 0.385, 0.177),
               "beta_abundance": (0.795, 0.089, 0.116), "gamma_lines": ((0.208, 0.111), (0.113, 0.062)),
               "default_grid": (81, 81, 81)},
+    "F18": {"name": "Fluorine-18", "symbol": "F18", "half_life": 1.8295, "beta_max": 0.634, "annihilation": 0.511,
+            "gamma_lines": (), "default_grid": (101, 101, 101)},
     "Ga68": {"name": "Gallium-68", "symbol": "Ga68", "half_life": 1.128, "beta_max": 1.899, "annihilation": 0.511,
              "gamma_lines": ((1.077, 0.03),), "default_grid": (151, 151, 151)},
 }
 
 # nuclides the reference registers (kernel_factory.py:15-22) but whose generators cannot run
-# (SURVEY.md Appendix B3): F18 helpers are `pass`, Tb161 is abstract, Ac225 calls an undefined method.
-REFERENCE_BROKEN = ("F18", "Tb161", "Ac225")
+# (SURVEY.md Appendix B3): Tb161 is abstract, Ac225 calls an undefined method.  (F18's helpers are `pass`
+# in the reference, f18_kernel.py:38-46; it is supplied here with the positron form of the Ga68 generator.)
+REFERENCE_BROKEN = ("Tb161", "Ac225")
 
 TISSUES = {
     "water": {"density": 1.0, "effective_Z": 7.42, "stopping_power_ratio": 1.0, "mu_by_rho": 0.096},

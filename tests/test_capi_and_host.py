@@ -115,7 +115,7 @@ def test_factory_errors_and_defaults():
     with pytest.raises(ValueError, match="Unsupported nuclide: Xx1"):
         f.get_kernel("Xx1", "water")
     with pytest.raises(ValueError, match="Supported:"):
-        f.get_kernel("F18", "water")
+        f.get_kernel("Tb161", "water")
     assert f._default_grid_sizes["Y90"] == (201, 201, 201) and f._default_grid_sizes["Lu177"] == (81, 81, 81)
 
 

@@ -109,7 +109,7 @@ def test_dose_calculator_front_door_modes():
     vs = (2.0, 2.0, 2.0)
     r = dc.calculate_dose(activity_maps=maps, time_points=t, voxel_size=vs)               # integration_mode="activity"
     acc = orc.integrate_activity_trapezoid([f64(m) for m in maps], t)
-    assert r.metadata["mode"] == "multi_timepoint_activity" and r.dose_rate_maps == []
+    assert r.metadata["mode"] == "multi_timepoint_activity" and len(r.dose_rate_maps) == 3
     assert orc.rel_err_of_peak(r.absorbed_dose, orc.conv_reference(acc, k)) <= TOL
     r = dc.calculate_dose(activity_maps=maps, time_points=t, voxel_size=vs, integration_mode="dose_rate")
     assert len(r.dose_rate_maps) == 3

@@ -8,13 +8,93 @@
 //     memory is only the exchange buffer between stages (ONE buffer, N*16*8 bytes, in place);
 //   * in the x pass the forward transform ends and the inverse transform starts in the same registers:
 //     forward -> multiply by the cached kernel spectrum -> inverse without touching memory;
-//   * all index arithmetic folds to shifts/immediates, inter-stage twiddles come from a shared-memory
-//     copy of the N-th roots table.
+//   * index arithmetic folds to immediates: a butterfly b reads indices b + (N/R)*j; inter-stage
+//     twiddles sit in shared memory as per-stage tables laid out [p][k] so one butterfly fetches its
+//     R-1 factors with R/2 128-bit loads; the inverse multiplies by the conjugate instead of negating.
 // Sizes outside the instantiated menu fall back to the generic engine in fft_passes.cuh.
 #pragma once
 #include "fft_passes.cuh"
 
 namespace pvd {
+
+__host__ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// Address helpers.  `opaque` hides a per-thread base pointer from the optimiser so that every access is
+// formed as base + (32-bit stride in bytes) * (compile-time count) = ONE IMAD.WIDE.U32, instead of being
+// re-derived from the kernel parameters with a 4-instruction 64-bit LEA sequence per access.
+template <class T>
+__device__ __forceinline__ T* opaque(T* p) {
+#ifndef PVD_EMULATE
+    asm volatile("" : "+l"(p));
+#endif
+    return p;
+}
+template <class T>
+__device__ __forceinline__ T* eptr(T* base, unsigned stride_bytes, int count) {
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(const_cast<typename std::remove_const<T>::type*>(base)) +
+                                (unsigned long long)stride_bytes * (unsigned)count);
+}
+
+// The opaque base pointers are generic as far as the compiler knows; these keep the accesses on the
+// global path (LDG/STG instead of generic LD/ST).
+__device__ __forceinline__ float2 ldg64(const float2* p) {
+#ifdef PVD_EMULATE
+    return *p;
+#else
+    float2 v;
+    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#endif
+}
+__device__ __forceinline__ float2 ldg64_ro(const float2* p) {  // data that is read-only for the whole kernel (spectrum)
+#ifdef PVD_EMULATE
+    return *p;
+#else
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#endif
+}
+__device__ __forceinline__ void stg64(float2* p, float2 v) {
+#ifdef PVD_EMULATE
+    *p = v;
+#else
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+#endif
+}
+
+// ---- per-stage twiddle tables ------------------------------------------------------------------
+// Stage (radix R, stride S) of a length-N transform multiplies output k of butterfly p by W_N^{p*S*k},
+// p in [0, M), M = N/(R*S).  Table row p holds k = 0..R-1, padded to an even count (16-byte rows).
+template <int R>
+constexpr int tw_row() { return R + (R & 1); }
+template <int N, int R, int S>
+constexpr int tw_size() { return (N / (R * S) > 1) ? (N / (R * S)) * tw_row<R>() : 0; }
+
+template <int N, int R, int S>
+__device__ __forceinline__ void build_stage_table(float2* dst, const float2* __restrict__ gtw) {
+    constexpr int M = N / (R * S), RP = tw_row<R>();
+    if constexpr (M > 1) {
+        for (int i = threadIdx.x; i < M * RP; i += blockDim.x) {
+            const int p = i / RP, k = i - p * RP;
+            dst[i] = (k < R) ? gtw[p * S * k] : make_float2(0.f, 0.f);
+        }
+    }
+}
+
+// Tables of one radix schedule (RA, RB, RC); RC == 1 means two stages.  Only non-final stages have twiddles.
+template <int N, int RA, int RB, int RC>
+struct Sched {
+    static constexpr int T1 = tw_size<N, RA, 1>();
+    static constexpr int T2 = (RC > 1) ? tw_size<N, RB, RA>() : 0;
+    static constexpr int TOTAL = T1 + T2;
+    static __device__ __forceinline__ void build(float2* dst, const float2* __restrict__ gtw) {
+        build_stage_table<N, RA, 1>(dst, gtw);
+        if constexpr (RC > 1) build_stage_table<N, RB, RA>(dst + T1, gtw);
+    }
+};
 
 // One Stockham DIF stage with radix R and stride S.  in(u, j, idx, w) -> float2, out(u, k, idx, w, v).
 // (u, j)/(u, k) are the register slots (compile-time after unrolling), idx the transform index, w the line.
@@ -25,6 +105,7 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
     constexpr int TPC = NT / W;        // butterflies of one line processed concurrently
     constexpr int BPT = (NB + TPC - 1) / TPC;
     constexpr bool GUARD = (NB % TPC) != 0;
+    constexpr int RP = tw_row<R>();
     static_assert(N % R == 0 && NB % S == 0 && NT % W == 0, "bad radix schedule");
     const int w = threadIdx.x % W;
     const int b0 = threadIdx.x / W;
@@ -33,9 +114,8 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
     for (int u = 0; u < BPT; ++u) {
         const int b = b0 + u * TPC;
         if (!GUARD || b < NB) {
-            const int p = b / S, q = b % S;
             PVD_UNROLL
-            for (int j = 0; j < R; ++j) a[u][j] = in(u, j, q + S * (p + M * j), w);
+            for (int j = 0; j < R; ++j) a[u][j] = in(u, j, b + NB * j, w);  // q + S*(p + M*j) == b + NB*j
         }
     }
     if (SYNC_AFTER_READ) __syncthreads();
@@ -43,24 +123,35 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
     for (int u = 0; u < BPT; ++u) {
         const int b = b0 + u * TPC;
         if (!GUARD || b < NB) {
-            const int p = b / S, q = b % S;
             Dft<R, DIR>::run(a[u]);
-            if (M > 1) {
+            int obase;  // q + S*R*p
+            if constexpr (S == 1) {
+                obase = R * b;
+            } else if constexpr (M == 1) {
+                obase = b;
+            } else {
+                obase = (b % S) + (R * S) * (b / S);
+            }
+            if constexpr (M > 1) {
+                const float4* __restrict__ tp = reinterpret_cast<const float4*>(tws + (b / S) * RP);
+                float4 tv[RP / 2];
+                PVD_UNROLL
+                for (int i = 0; i < RP / 2; ++i) tv[i] = tp[i];
                 PVD_UNROLL
                 for (int k = 1; k < R; ++k) {
-                    float2 t = tws[p * S * k];
-                    if (DIR > 0) t.y = -t.y;
-                    a[u][k] = cmul(a[u][k], t);
+                    const float2 t = (k & 1) ? make_float2(tv[k / 2].z, tv[k / 2].w) : make_float2(tv[k / 2].x, tv[k / 2].y);
+                    a[u][k] = (DIR < 0) ? cmul(a[u][k], t) : cmulc(a[u][k], t);
                 }
             }
             PVD_UNROLL
-            for (int k = 0; k < R; ++k) out(u, k, q + S * (R * p + k), w, a[u][k]);
+            for (int k = 0; k < R; ++k) out(u, k, obase + S * k, w, a[u][k]);
         }
     }
 }
 
 // Whole transform.  Stage list (R1, R2, R3) with R3 == 1 meaning two stages.  IN_SMEM / OUT_SMEM say
 // whether `in` / `out` address the exchange tile itself (then reads must complete before writes).
+// `tws` = Sched<N,R1,R2,R3> tables.
 template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out>
 __device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws) {
     static_assert(R1 * R2 * R3 == N, "radix schedule must multiply to N");
@@ -69,7 +160,7 @@ __device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const
     fast_stage<N, W, NT, R1, 1, DIR, IN_SMEM>(in, sm_out, tws);
     __syncthreads();
     if constexpr (R3 > 1) {
-        fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws);
+        fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1);
         __syncthreads();
         fast_stage<N, W, NT, R3, R1 * R2, DIR, OUT_SMEM>(sm_in, out, tws);
     } else {
@@ -77,67 +168,83 @@ __device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const
     }
 }
 
+// Radix of the last stage and the register-slot geometry of its outputs.
+template <int N, int NT, int R1, int R2, int R3>
+struct LastStage {
+    static constexpr int RL = (R3 > 1) ? R3 : R2;
+    static constexpr int STEP = N / RL;            // output index of slot (u, k) = b0 + u*TPC + STEP*k
+    static constexpr int TPC = NT / 16;
+    static constexpr int BPT = (STEP + TPC - 1) / TPC;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Column passes (axis 1 forward / inverse, axis 0 forward * spectrum * inverse, kernel spectrum).
+// One tile per CTA; used where the double-buffered persistent variant (fft_pipe.cuh) does not fit.
 template <int N, int NT, int R1, int R2, int R3, int MODE>
 __global__ void __launch_bounds__(NT) cols_fast_kernel(const ColArgs g) {
     constexpr int W = 16;
-    constexpr int RL = (R3 > 1) ? R3 : R2;  // radix of the last forward stage
-    constexpr int TPC = NT / W;
-    constexpr int BPTL = (N / RL + TPC - 1) / TPC;
+    using LS_ = LastStage<N, NT, R1, R2, R3>;
+    constexpr int RL = LS_::RL, TPC = LS_::TPC, BPTL = LS_::BPT;
+    using Fwd = Sched<N, R1, R2, R3>;
+    using Rev = Sched<N, (R3 > 1 ? R3 : R2), (R3 > 1 ? R2 : R1), (R3 > 1 ? R1 : 1)>;
+    constexpr bool SYM = (R3 > 1) ? (R1 == R3) : (R1 == R2);
     PVD_DYN_SMEM(float2, smem);
     float2* tile = smem;
     float2* tws = smem + N * W;
-    for (int i = threadIdx.x; i < N; i += NT) tws[i] = g.tw[i];
+    float2* twr = SYM ? tws : tws + Fwd::TOTAL;
+    Fwd::build(tws, g.tw);
+    if constexpr (MODE == COL_CONV && !SYM) Rev::build(twr, g.tw);
     const int z0 = blockIdx.x * W;
     const long long base = (long long)(g.outer0 + (int)blockIdx.y) * g.os + z0;
     const int zlim = g.nzf - z0;
-    const float2* __restrict__ src = g.in + base;
-    float2* __restrict__ dst = g.out + base;
-    const long long es = g.es;
-    const int n_in = g.n_in, lo = g.out_lo, hi = g.out_lo + g.out_n;
-    auto gin = [&](int, int, int r, int w) -> float2 {
-        return (r < n_in && w < zlim) ? src[(long long)r * es + w] : make_float2(0.f, 0.f);
+    const unsigned es = (unsigned)g.es;
+    const unsigned esb = es * (unsigned)sizeof(float2);  // stride between transform indices in bytes
+    const int wl = threadIdx.x % W, b0 = threadIdx.x / W;
+    const bool wok = wl < zlim;
+    const float2* src = opaque(g.in + base + (size_t)b0 * es + wl);
+    float2* dst = opaque(g.out + base + (size_t)b0 * es + wl);
+    const int n_in = g.n_in;
+    const unsigned cnt = (unsigned)g.out_n;
+    const int blo = b0 - g.out_lo;
+    constexpr int NB1 = N / R1;
+    auto gin = [&](int u, int j, int r, int) -> float2 {
+        return (wok && r < n_in) ? ldg64(eptr(src, esb, u * TPC + NB1 * j)) : make_float2(0.f, 0.f);
     };
-    __syncthreads();  // twiddle table visible
-    if constexpr (MODE == COL_FWD || MODE == COL_SPEC) {
-        const float sc = g.scale;
-        auto gout = [&](int, int, int r, int w, float2 v) {
-            if (MODE == COL_SPEC) v = make_float2(v.x * sc, v.y * sc);
-            if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = v;
-        };
+    auto gout = [&](int u, int k, int, int, float2 v) {
+        if (wok && (unsigned)(blo + u * TPC + LS_::STEP * k) < cnt) stg64(eptr(dst, esb, u * TPC + LS_::STEP * k), v);
+    };
+    __syncthreads();  // twiddle tables visible
+    if constexpr (MODE == COL_FWD) {
         fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, gout, tile, tws);
+    } else if constexpr (MODE == COL_SPEC) {
+        const float sc = g.scale;
+        auto sout = [&](int u, int k, int r, int w, float2 v) { gout(u, k, r, w, make_float2(v.x * sc, v.y * sc)); };
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, sout, tile, tws);
     } else if constexpr (MODE == COL_INV) {
-        auto gout = [&](int, int, int r, int w, float2 v) {
-            if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = v;
-        };
         fast_fft<N, W, W, NT, +1, R1, R2, R3, false, false>(gin, gout, tile, tws);
     } else {  // COL_CONV: forward -> * spectrum -> inverse, the middle never leaves registers
         float2 hold[BPTL][RL];
         auto rout = [&](int u, int k, int, int, float2 v) { hold[u][k] = v; };
         fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, rout, tile, tws);
-        const float2* __restrict__ sp = g.spec + base;
-        const int wl = threadIdx.x % W, b0 = threadIdx.x / W;
+        const float2* sp = opaque(g.spec + base + (size_t)b0 * es + wl);
         PVD_UNROLL
         for (int u = 0; u < BPTL; ++u) {
-            const int b = b0 + u * TPC;
-            if (b < N / RL) {
+            if (b0 + u * TPC < LS_::STEP) {
                 PVD_UNROLL
-                for (int k = 0; k < RL; ++k) {
-                    const int r = b + (N / RL) * k;
-                    if (wl < zlim) hold[u][k] = cmul(hold[u][k], __ldg(&sp[(long long)r * es + wl]));
-                }
+                for (int k = 0; k < RL; ++k)
+                    if (wok) hold[u][k] = cmul(hold[u][k], ldg64_ro(eptr(sp, esb, u * TPC + LS_::STEP * k)));
             }
         }
         __syncthreads();  // every thread finished reading the tile in the last forward stage
         auto rin = [&](int u, int j, int, int) -> float2 { return hold[u][j]; };
-        auto gout = [&](int, int, int r, int w, float2 v) {
-            if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = v;
+        constexpr int STEPR = N / R1;  // the reversed schedule ends with radix R1
+        auto gout_rev = [&](int u, int k, int, int, float2 v) {
+            if (wok && (unsigned)(blo + u * TPC + STEPR * k) < cnt) stg64(eptr(dst, esb, u * TPC + STEPR * k), v);
         };
         if constexpr (R3 > 1)
-            fast_fft<N, W, W, NT, +1, R3, R2, R1, false, false>(rin, gout, tile, tws);
+            fast_fft<N, W, W, NT, +1, R3, R2, R1, false, false>(rin, gout_rev, tile, twr);
         else
-            fast_fft<N, W, W, NT, +1, R2, R1, 1, false, false>(rin, gout, tile, tws);
+            fast_fft<N, W, W, NT, +1, R2, R1, 1, false, false>(rin, gout_rev, tile, twr);
     }
 }
 
@@ -150,7 +257,7 @@ __global__ void __launch_bounds__(NT) rows_fwd_fast_kernel(const RowFwdArgs g) {
     PVD_DYN_SMEM(float2, smem);
     float2* tile = smem;
     float2* tws = smem + N * LS;
-    for (int i = threadIdx.x; i < N; i += NT) tws[i] = g.tw[i];
+    Sched<N, R1, R2, R3>::build(tws, g.tw);
     const long long nrows = (long long)g.n0 * g.n1;
     const long long row0 = (long long)blockIdx.x * (2 * W);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -208,7 +315,7 @@ __global__ void __launch_bounds__(NT) rows_inv_fast_kernel(const RowInvArgs g) {
     PVD_DYN_SMEM(float2, smem);
     float2* tile = smem;
     float2* tws = smem + N * LS;
-    for (int i = threadIdx.x; i < N; i += NT) tws[i] = g.tw[i];
+    Sched<N, R1, R2, R3>::build(tws, g.tw);
     const long long nrows = (long long)g.O0 * g.O1;
     const long long row0 = (long long)blockIdx.x * (2 * W);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -33,78 +33,84 @@ struct ColPipeArgs {
     ColArgs c;
     int ntz;     // tiles along the frequency axis
     int ntiles;  // ntz * number of outer indices
+    unsigned ntz_magic;  // ceil(2^32 / ntz): t / ntz == __umulhi(t, magic) for t * ntz < 2^32
 };
 
 template <int N, int NT, int MINB, int R1, int R2, int R3, int MODE>
 __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const ColPipeArgs pa) {
     constexpr int W = 16;
-    constexpr int RL = (R3 > 1) ? R3 : R2;
-    constexpr int TPC = NT / W;
-    constexpr int BPTL = (N / RL + TPC - 1) / TPC;
+    using LS_ = LastStage<N, NT, R1, R2, R3>;
+    constexpr int RL = LS_::RL, TPC = LS_::TPC, BPTL = LS_::BPT;
+    using Fwd = Sched<N, R1, R2, R3>;
+    using Rev = Sched<N, (R3 > 1 ? R3 : R2), (R3 > 1 ? R2 : R1), (R3 > 1 ? R1 : 1)>;
+    constexpr bool SYM = (R3 > 1) ? (R1 == R3) : (R1 == R2);
     constexpr int CHUNKS = N * 8;  // 16-byte chunks per tile
     static_assert(CHUNKS % NT == 0 && NT % 8 == 0, "tile must split evenly over the threads");
     const ColArgs& g = pa.c;
     PVD_DYN_SMEM(float2, smem);
     float2* tws = smem + 2 * N * W;
-    for (int i = threadIdx.x; i < N; i += NT) tws[i] = g.tw[i];
-    const long long es = g.es;
-    const int n_in = g.n_in, lo = g.out_lo, hi = g.out_lo + g.out_n;
+    float2* twr = SYM ? tws : tws + Fwd::TOTAL;
+    Fwd::build(tws, g.tw);
+    if constexpr (MODE == COL_CONV && !SYM) Rev::build(twr, g.tw);
+    const unsigned es = (unsigned)g.es;
+    const unsigned esb = es * (unsigned)sizeof(float2);
+    const int n_in = g.n_in;
+    const unsigned cnt = (unsigned)g.out_n;
     const int ntz = pa.ntz, ntiles = pa.ntiles;
     const int crow = threadIdx.x >> 3, ccol = (threadIdx.x & 7) * 2;  // this thread's chunk inside a row group
-    auto tile_base = [&](int t) -> long long {
-        const int zt = t % ntz, outer = t / ntz;
+    const int wl = threadIdx.x % W, b0 = threadIdx.x / W;
+    const int blo = b0 - g.out_lo;
+    const size_t toff = (size_t)b0 * es + wl;  // this thread's element inside a tile (stage-1 input / last-stage output)
+    const unsigned magic = pa.ntz_magic;
+    auto tile_base = [&](int t, int& zt) -> long long {
+        const int outer = (ntz == 1) ? t : (int)__umulhi((unsigned)t, magic);
+        zt = t - outer * ntz;
         return (long long)(g.outer0 + outer) * g.os + (long long)zt * W;
     };
+    const size_t coff = (size_t)crow * es + ccol;
     auto issue = [&](float2* buf, int t) {
-        const float2* src = g.in + tile_base(t) + (long long)crow * es + ccol;
+        int zt;
+        const float2* src = opaque(g.in + tile_base(t, zt) + coff);
         float2* dstp = buf + crow * W + ccol;
         PVD_UNROLL
-        for (int i = 0; i < CHUNKS / NT; ++i) {
-            const int r = crow + i * (NT / 8);
-            cp_async16(dstp, src, r < n_in);
-            src += (long long)(NT / 8) * es;
-            dstp += (NT / 8) * W;
-        }
+        for (int i = 0; i < CHUNKS / NT; ++i)
+            cp_async16(dstp + i * ((NT / 8) * W), eptr(src, esb, i * (NT / 8)), crow + i * (NT / 8) < n_in);
     };
     int t = blockIdx.x;
     if (t < ntiles) issue(smem, t);
     cp_async_commit();
     int cur = 0;
-    const int wl = threadIdx.x % W, b0 = threadIdx.x / W;
     for (; t < ntiles; t += gridDim.x) {
         const int tn = t + gridDim.x;
         if (tn < ntiles) issue(smem + (cur ^ 1) * (N * W), tn);
         cp_async_commit();
-        const long long base = tile_base(t);
-        const int zlim = g.nzf - (t % ntz) * W;
-        float2* __restrict__ dst = g.out + base;
+        int zt;
+        const long long base = tile_base(t, zt);
+        const bool wok = wl < g.nzf - zt * W;
+        float2* dst = opaque(g.out + base + toff);
         float2 sp[BPTL][RL];
         if constexpr (MODE == COL_CONV) {  // spectrum tile -> registers, consumed after the forward transform
-            const float2* __restrict__ spp = g.spec + base;
+            const float2* spp = opaque(g.spec + base + toff);
             PVD_UNROLL
             for (int u = 0; u < BPTL; ++u) {
-                const int b = b0 + u * TPC;
                 PVD_UNROLL
-                for (int k = 0; k < RL; ++k) {
-                    const int r = b + (N / RL) * k;
-                    sp[u][k] = (b < N / RL && wl < zlim) ? __ldg(&spp[(long long)r * es + wl]) : make_float2(0.f, 0.f);
-                }
+                for (int k = 0; k < RL; ++k)
+                    sp[u][k] = (wok && b0 + u * TPC < LS_::STEP) ? ldg64_ro(eptr(spp, esb, u * TPC + LS_::STEP * k))
+                                                                  : make_float2(0.f, 0.f);
             }
         }
         cp_async_wait<1>();  // everything but the prefetch just issued has landed
         __syncthreads();
         float2* tile = smem + cur * (N * W);
         auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * W + w]; };
-        auto gout = [&](int, int, int r, int w, float2 v) {
-            if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = v;
+        auto gout = [&](int u, int k, int, int, float2 v) {
+            if (wok && (unsigned)(blo + u * TPC + LS_::STEP * k) < cnt) stg64(eptr(dst, esb, u * TPC + LS_::STEP * k), v);
         };
         if constexpr (MODE == COL_FWD) {
             fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(sm_in, gout, tile, tws);
         } else if constexpr (MODE == COL_SPEC) {
             const float sc = g.scale;
-            auto sout = [&](int, int, int r, int w, float2 v) {
-                if (r >= lo && r < hi && w < zlim) dst[(long long)r * es + w] = make_float2(v.x * sc, v.y * sc);
-            };
+            auto sout = [&](int u, int k, int r, int w, float2 v) { gout(u, k, r, w, make_float2(v.x * sc, v.y * sc)); };
             fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(sm_in, sout, tile, tws);
         } else if constexpr (MODE == COL_INV) {
             fast_fft<N, W, W, NT, +1, R1, R2, R3, true, false>(sm_in, gout, tile, tws);
@@ -119,10 +125,14 @@ __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const ColPipeArgs p
             }
             __syncthreads();  // all reads of the tile by the last forward stage are done
             auto rin = [&](int u, int j, int, int) -> float2 { return hold[u][j]; };
+            constexpr int STEPR = N / R1;  // the reversed schedule ends with radix R1
+            auto gout_rev = [&](int u, int k, int, int, float2 v) {
+                if (wok && (unsigned)(blo + u * TPC + STEPR * k) < cnt) stg64(eptr(dst, esb, u * TPC + STEPR * k), v);
+            };
             if constexpr (R3 > 1)
-                fast_fft<N, W, W, NT, +1, R3, R2, R1, false, false>(rin, gout, tile, tws);
+                fast_fft<N, W, W, NT, +1, R3, R2, R1, false, false>(rin, gout_rev, tile, twr);
             else
-                fast_fft<N, W, W, NT, +1, R2, R1, 1, false, false>(rin, gout, tile, tws);
+                fast_fft<N, W, W, NT, +1, R2, R1, 1, false, false>(rin, gout_rev, tile, twr);
         }
         __syncthreads();  // tile buffer may be refilled by the next iteration's prefetch
         cur ^= 1;

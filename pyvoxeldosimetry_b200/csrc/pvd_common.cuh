@@ -52,6 +52,7 @@ inline thread_local Ctx ctx;
 static inline void __syncthreads() { pvd_emu::ctx.bar->arrive_and_wait(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline void sincospi(double x, double* s, double* c) {
     *s = std::sin(M_PI * x);
     *c = std::cos(M_PI * x);

@@ -10,6 +10,7 @@
 #include "elementwise.cuh"
 #include "fft_fast.cuh"
 #include "fft_pipe.cuh"
+#include "fft_rows_pipe.cuh"
 #include "fft_passes.cuh"
 
 using namespace pvd;
@@ -124,6 +125,9 @@ struct FastRows {
     int N, NT;
     RowFwdKernelFn fwd;
     RowInvKernelFn inv;
+    RowFwdKernelFn fwdPipe;  // persistent cp.async-staged variants (fft_rows_pipe.cuh)
+    RowInvKernelFn invPipe;
+    size_t smemPipe;
 };
 #define PVD_COLS_FN(N, NT, R1, R2, R3)                                                             \
     {                                                                                                  \
@@ -137,8 +141,12 @@ struct FastRows {
     }
 #define PVD_COLS(N, NT, MINB, R1, R2, R3) { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), PVD_COLS_PIPE(N, NT, MINB, R1, R2, R3) }
 #define PVD_COLS_NOPIPE(N, NT, R1, R2, R3) { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), {nullptr, nullptr, nullptr, nullptr} }
-#define PVD_ROWS(N, NT, R1, R2, R3) \
-    { N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3> }
+#define PVD_ROWS(N, NT, MINB, R1, R2, R3)                                                                  \
+    {                                                                                                      \
+        N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>,           \
+            rows_fwd_pipe_kernel<N, NT, MINB, R1, R2, R3>, rows_inv_pipe_kernel<N, NT, MINB, R1, R2, R3>,  \
+            (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES + Sched<N, R1, R2, R3>::TOTAL * sizeof(float2) \
+    }
 const FastCols kFastCols[] = {
     PVD_COLS(512, 512, 1, 8, 8, 8),
     PVD_COLS(256, 256, 2, 16, 16, 1),
@@ -146,9 +154,9 @@ const FastCols kFastCols[] = {
     PVD_COLS_NOPIPE(1024, 1024, 16, 8, 8),
 };
 const FastRows kFastRows[] = {
-    PVD_ROWS(400, 320, 20, 20, 1),
-    PVD_ROWS(256, 256, 16, 16, 1),
-    PVD_ROWS(512, 512, 8, 8, 8),
+    PVD_ROWS(400, 320, 2, 20, 20, 1),
+    PVD_ROWS(256, 256, 3, 16, 16, 1),
+    PVD_ROWS(512, 512, 1, 8, 8, 8),
 };
 const FastCols* find_fast_cols(int n) {
     for (const auto& e : kFastCols)
@@ -174,6 +182,7 @@ struct pvd_plan {
     const FastRows* fastRows = nullptr;
     bool usePipe = true;
     int pipeGrid[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // persistent grid size per axis / mode
+    int rowPipeGrid[2] = {0, 0};                        // persistent grid size of the row passes (fwd, inv)
     size_t off_tw[3], off_buf, off_spec, off_flag, ws_bytes;
     char* ws = nullptr;
     bool kernel_set = false;
@@ -228,9 +237,17 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
     const long long per = 2LL << p->rowLlog;
     const long long nblk = (nrows + per - 1) / per;
     if (nblk <= 0) return PVD_OK;
+    if (p->fastRows && p->usePipe && p->rowPipeGrid[0] > 0 && T == 1 && nrows < 2000000000LL && s0 % 4 == 0 && s1 % 4 == 0 &&
+        ((uintptr_t)in[0] & 15) == 0) {
+        const FastRows* f = p->fastRows;
+        const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[0]);
+        PVD_LAUNCH(f->fwdPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
+        PVD_CUDA_CHECK("rows_fwd_pipe_kernel");
+        return PVD_OK;
+    }
     if (p->fastRows) {
         const FastRows* f = p->fastRows;
-        const size_t smem = ((size_t)f->N * 17 + f->N) * sizeof(float2);
+        const size_t smem = ((size_t)f->N * 17 + 4 * f->N) * sizeof(float2);
         PVD_LAUNCH(f->fwd, dim3((unsigned)((nrows + 31) / 32)), dim3(f->NT), smem, stream, a);
         PVD_CUDA_CHECK("rows_fwd_fast_kernel");
         return PVD_OK;
@@ -269,7 +286,9 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
         pa.c = a;
         pa.ntz = (p->Nh + 15) / 16;
         pa.ntiles = pa.ntz * nouter;
-        const size_t smem = ((size_t)f->N * 32 + f->N) * sizeof(float2);
+        pa.ntz_magic = (unsigned)((0x100000000ULL + pa.ntz - 1) / pa.ntz);  // exact for t * ntz < 2^32 (ntz == 1: magic wraps to 0)
+        if (pa.ntz == 1) pa.ntz_magic = 0xFFFFFFFFu;
+        const size_t smem = ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2);
         const int grid = std::min(pa.ntiles, p->pipeGrid[axis][mode]);
         PVD_LAUNCH(f->pipe[mode], dim3((unsigned)grid), dim3(f->NT), smem, stream, pa);
         PVD_CUDA_CHECK("cols_pipe_kernel");
@@ -277,7 +296,7 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
     }
     if (p->fastCols[axis]) {
         const FastCols* f = p->fastCols[axis];
-        const size_t smem = ((size_t)f->N * 16 + f->N) * sizeof(float2);
+        const size_t smem = ((size_t)f->N * 16 + 4 * f->N) * sizeof(float2);
         PVD_LAUNCH(f->fn[mode], dim3((unsigned)((p->Nh + 15) / 16), (unsigned)nouter), dim3(f->NT), smem, stream, a);
         PVD_CUDA_CHECK("cols_fast_kernel");
         return PVD_OK;
@@ -336,6 +355,8 @@ int plan_finish(pvd_plan* p) {
     if (!(force && force[0] == '1')) {
         for (int a = 0; a < 2; ++a) p->fastCols[a] = find_fast_cols(p->m[a]);
         p->fastRows = find_fast_rows(p->m[2]);
+        // the specialised column kernels index the work buffer with 32-bit element offsets
+        if ((double)p->m[0] * p->m[1] * p->Sz >= 2147483648.0) p->fastCols[0] = p->fastCols[1] = nullptr;
     }
     const char* nopipe = getenv("PVD_NO_PIPE");
     p->usePipe = !(nopipe && nopipe[0] == '1');
@@ -444,12 +465,24 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
                     int dev = 0, sms = 0, per = 0;
                     cudaGetDevice(&dev);
                     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->pipe[md], f->NT, ((size_t)f->N * 32 + f->N) * sizeof(float2));
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->pipe[md], f->NT, ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2));
                     p->pipeGrid[a][md] = sms * per;  // one resident wave: every CTA stays on its SM and loops
                 }
             }
     if (p->fastRows && (PVD_SET_SMEM(p->fastRows->fwd, kMaxSmem) != 0 || PVD_SET_SMEM(p->fastRows->inv, kMaxSmem) != 0))
         return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (rows)");
+    if (p->fastRows && p->fastRows->smemPipe <= kMaxSmem) {
+        const FastRows* f = p->fastRows;
+        if (PVD_SET_SMEM(f->fwdPipe, kMaxSmem) != 0 || PVD_SET_SMEM(f->invPipe, kMaxSmem) != 0)
+            return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (rows pipe)");
+        int dev = 0, sms = 0, per = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->fwdPipe, f->NT, f->smemPipe);
+        p->rowPipeGrid[0] = sms * per;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->invPipe, f->NT, f->smemPipe);
+        p->rowPipeGrid[1] = sms * per;
+    }
     if (PVD_SET_SMEM(rows_fwd_kernel, kMaxSmem) != 0 || PVD_SET_SMEM(rows_inv_kernel, kMaxSmem) != 0 ||
         PVD_SET_SMEM(cols_kernel, kMaxSmem) != 0) {
         cudaGetLastError();
@@ -540,9 +573,18 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     a.st = p->st[2];
     const long long nrows = (long long)p->on[0] * p->on[1];
     const long long per = 2LL << p->rowLlog;
+    if (p->fastRows && p->usePipe && p->rowPipeGrid[1] > 0 && nrows < 2000000000LL &&
+        (!density || (((uintptr_t)density & 15) == 0 && a.den_s0 % 4 == 0 && a.den_s1 % 4 == 0))) {
+        const FastRows* f = p->fastRows;
+        const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[1]);
+        PVD_LAUNCH(f->invPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
+        PVD_CUDA_CHECK("rows_inv_pipe_kernel");
+        p->mark_end(stream);
+        return PVD_OK;
+    }
     if (p->fastRows) {
         const FastRows* f = p->fastRows;
-        const size_t smem = ((size_t)f->N * 17 + f->N) * sizeof(float2);
+        const size_t smem = ((size_t)f->N * 17 + 4 * f->N) * sizeof(float2);
         PVD_LAUNCH(f->inv, dim3((unsigned)((nrows + 31) / 32)), dim3(f->NT), smem, stream, a);
         PVD_CUDA_CHECK("rows_inv_fast_kernel");
         p->mark_end(stream);

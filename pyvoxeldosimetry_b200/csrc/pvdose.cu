@@ -10,6 +10,7 @@
 #include "elementwise.cuh"
 #include "fft_fast.cuh"
 #include "fft_pipe.cuh"
+#include "fft_pipe2.cuh"
 #include "fft_rows_pipe.cuh"
 #include "fft_passes.cuh"
 
@@ -120,6 +121,7 @@ struct FastCols {
     int N, NT;
     ColKernelFn fn[4];        // one tile per CTA, indexed by ColMode
     ColPipeKernelFn pipe[4];  // persistent cp.async-pipelined variant (null when the double buffer does not fit)
+    int pipeNT[4];            // threads per CTA of each pipelined variant
 };
 struct FastRows {
     int N, NT;
@@ -139,8 +141,26 @@ struct FastRows {
         cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_FWD>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_INV>,    \
             cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_CONV>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC> \
     }
-#define PVD_COLS(N, NT, MINB, R1, R2, R3) { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), PVD_COLS_PIPE(N, NT, MINB, R1, R2, R3) }
-#define PVD_COLS_NOPIPE(N, NT, R1, R2, R3) { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), {nullptr, nullptr, nullptr, nullptr} }
+#define PVD_COLS(N, NT, MINB, R1, R2, R3) \
+    { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), PVD_COLS_PIPE(N, NT, MINB, R1, R2, R3), {NT, NT, NT, NT} }
+// NTC threads for the (issue-bound) forward*spectrum*inverse variant, NT for the others
+#define PVD_COLS_C(N, NT, MINB, NTC, R1, R2, R3)                                                                \
+    {                                                                                                           \
+        N, NT, PVD_COLS_FN(N, NT, R1, R2, R3),                                                                  \
+            {cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_FWD>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_INV>, \
+             cols_pipe_kernel<N, NTC, 1, R1, R2, R3, COL_CONV>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC>}, \
+            {NT, NT, NTC, NT}                                                                                   \
+    }
+// persistent variant with two columns per thread (fft_pipe2.cuh)
+#define PVD_COLS_P2(N, NT, MINB, R1, R2, R3)                                                                        \
+    {                                                                                                               \
+        N, NT, PVD_COLS_FN(N, NT, R1, R2, R3),                                                                      \
+            {cols_pipe2_kernel<N, NT, MINB, R1, R2, R3, COL_FWD>, cols_pipe2_kernel<N, NT, MINB, R1, R2, R3, COL_INV>, \
+             cols_pipe2_kernel<N, NT, MINB, R1, R2, R3, COL_CONV>, cols_pipe2_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC>}, \
+            {NT, NT, NT, NT}                                                                                        \
+    }
+#define PVD_COLS_NOPIPE(N, NT, R1, R2, R3) \
+    { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), {nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0} }
 #define PVD_ROWS(N, NT, MINB, R1, R2, R3)                                                                  \
     {                                                                                                      \
         N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>,           \
@@ -290,7 +310,7 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
         if (pa.ntz == 1) pa.ntz_magic = 0xFFFFFFFFu;
         const size_t smem = ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2);
         const int grid = std::min(pa.ntiles, p->pipeGrid[axis][mode]);
-        PVD_LAUNCH(f->pipe[mode], dim3((unsigned)grid), dim3(f->NT), smem, stream, pa);
+        PVD_LAUNCH(f->pipe[mode], dim3((unsigned)grid), dim3(f->pipeNT[mode]), smem, stream, pa);
         PVD_CUDA_CHECK("cols_pipe_kernel");
         return PVD_OK;
     }
@@ -465,7 +485,7 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
                     int dev = 0, sms = 0, per = 0;
                     cudaGetDevice(&dev);
                     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->pipe[md], f->NT, ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2));
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->pipe[md], f->pipeNT[md], ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2));
                     p->pipeGrid[a][md] = sms * per;  // one resident wave: every CTA stays on its SM and loops
                 }
             }

@@ -176,3 +176,40 @@ def test_elementwise_ops(lib):
     d, r = rng.uniform(0, 1, 300).astype(np.float32), rng.uniform(0, 2, 300).astype(np.float32)
     lib.density_scale(d.ctypes.data, r.ctypes.data, 1.0, 0.1, 0.05, 2.0, out.ctypes.data, 300)
     np.testing.assert_allclose(out[:300], orc.density_correct(2.0 * d.astype(np.float64), r, 1.0, 0.1, 0.05), rtol=1e-6)
+
+
+# ---- size-specialised + persistent pipelined kernels (lengths on the menu: 512, 256, 400) ----------
+FAST_CASES = [
+    ((512, 3, 6), (5, 2, 3), 0, 2, True),      # x pass: cols_pipe_kernel<512> CONV, ntz == 1
+    ((5, 40, 400), (2, 5, 7), 0, 1, True),     # rows pipe kernels <400>, 7 tiles over 3 emulated SMs
+    ((3, 256, 5), (3, 9, 3), 0, 2, False),     # y pass <256>
+    ((256, 2, 256), (4, 2, 9), 0, 1, True),    # x <256>, rows <256>, several tiles per CTA
+    ((4, 33, 376), (1, 3, 41), 1, 1, True),    # same mode: 376 -> 400 partial cp.async zero fill
+    ((3, 35, 379), (1, 3, 41), 1, 1, True),    # n2 % 4 != 0 -> unaligned rows fall back to the LDG kernel
+    ((500, 2, 4), (25, 1, 3), 1, 1, False),    # same mode along x: 500 -> 512, crop offset 12
+]
+
+
+@pytest.mark.parametrize("shape,kshape,boundary,T,den", FAST_CASES)
+@pytest.mark.parametrize("variant", ["pipe", "nopipe", "generic"])
+def test_fast_and_pipelined_kernels(lib, monkeypatch, shape, kshape, boundary, T, den, variant):
+    if variant == "generic" and shape[0] * shape[1] * shape[2] > 40000:
+        pytest.skip("generic engine already covered on small shapes")
+    monkeypatch.setenv("PVD_NO_PIPE", "1" if variant == "nopipe" else "0")
+    monkeypatch.setenv("PVD_FORCE_GENERIC", "1" if variant == "generic" else "0")
+    rng = np.random.default_rng(abs(hash((shape, kshape, boundary))) % 2**32)
+    maps = [rng.uniform(0, 1e3, shape) for _ in range(T)]
+    maps[0][tuple(s // 2 for s in shape)] = 2e6
+    w = [0.25, 0.75][:T] if T > 1 else None
+    k = rng.uniform(0, 1, kshape)
+    rho = rng.uniform(0.2, 2.0, shape) if den else None
+    p = EmuConv(lib, shape, kshape, boundary)
+    p.set_kernel(k)
+    got = p.execute(maps, w, rho)
+    p.close()
+    f = lambda x: np.asarray(x, np.float32).astype(np.float64)
+    acc = f(maps[0]) if T == 1 else sum(np.float64(np.float32(wi)) * f(m) for wi, m in zip(w, maps))
+    ref = orc.conv_reference(acc, f(k)) if boundary == 0 else orc.conv_same(acc, f(k))
+    if den:
+        ref = orc.density_correct(ref, f(rho))
+    assert orc.rel_err_of_peak(got, ref) <= TOL

@@ -8,7 +8,7 @@ Reference semantics kept by default:
     (kernel_convolution.py:94-106), evaluated as ONE convolution of sum_i w_i a_i (linearity);
   * the kernel is the factory's 64^3 grid at ``kernel_resolution`` (kernel_convolution.py:39-46).
 Config keys (all optional): boundary ('reference'|'same'), kernel_grid, device, output_dtype
-('float32'|'float64'), rho_ref, rho_min, rho_cut, scale, strict_reference.
+('float32'|'float64'), rho_ref, rho_min, rho_cut, scale, strict_reference, algo ('auto'|'fft'|'direct').
 Repairs over the reference are listed in SURVEY.md section 8b; `strict_reference=True` turns the
 behavioural ones off (the resample stub then raises instead of crashing with AttributeError).
 """
@@ -56,6 +56,8 @@ class KernelConvolutionCalculator(DosimetryCalculator):
             raise ValueError(f"unknown boundary mode {self.boundary!r} (use 'reference' or 'same')")
         self.kernel_grid = tuple(self.config.get("kernel_grid", (64, 64, 64)))  # kernel_convolution.py:45
         self.strict_reference = bool(self.config.get("strict_reference", False))
+        # 'auto' picks the direct TMA-tiled convolution for small kernels in 'same' mode, the FFT path otherwise
+        self.algo = {"auto": 0, "fft": 1, "direct": 2}[str(self.config.get("algo", "auto"))]
         self._plans = engine.PlanCache(capacity=int(self.config.get("plan_cache", 4)))
         self._kernel_version = 0
         self._kernel_host: Optional[np.ndarray] = None
@@ -114,7 +116,7 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         if any(tuple(m.shape) != shape for m in maps):
             raise ValueError("All activity maps must have the same dimensions")
         kdev, tag = self._kernel_for(voxel_size)
-        plan = self._plans.get(shape, tuple(kdev.shape), self.boundary, self.device, tag, lambda: kdev)
+        plan = self._plans.get(shape, tuple(kdev.shape), self.boundary, self.device, tag, lambda: kdev, self.algo)
         acts = [engine.to_device_f32(m, self.device) for m in maps]
         den = None
         if tissue_densities is not None:

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "direct_conv.cuh"
 #include "elementwise.cuh"
 #include "fft_fast.cuh"
 #include "fft_pipe.cuh"
@@ -203,6 +204,11 @@ struct pvd_plan {
     bool usePipe = true;
     int pipeGrid[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // persistent grid size per axis / mode
     int rowPipeGrid[2] = {0, 0};                        // persistent grid size of the row passes (fwd, inv)
+    // direct (TMA) path
+    int want_algo = PVD_ALGO_AUTO;
+    int dbox[3] = {0, 0, 0};
+    size_t off_taps = 0, dsmem = 0;
+    float* taps() const { return reinterpret_cast<float*>(ws + off_taps); }
     size_t off_tw[3], off_buf, off_spec, off_flag, ws_bytes;
     char* ws = nullptr;
     bool kernel_set = false;
@@ -380,6 +386,96 @@ int plan_finish(pvd_plan* p) {
     }
     const char* nopipe = getenv("PVD_NO_PIPE");
     p->usePipe = !(nopipe && nopipe[0] == '1');
+    // ---- direct tiled convolution (TMA halo tiles): 'same'-type geometry, small kernels only
+    bool direct_ok = (p->k[2] == 3 || p->k[2] == 5 || p->k[2] == 7) && p->k[0] <= 9 && p->k[1] <= 9 && p->n[2] % 4 == 0;
+    for (int i = 0; i < 3; ++i) direct_ok = direct_ok && p->on[i] == p->n[i] && p->olo[i] == p->k[i] / 2;
+    const long long taps = (long long)p->k[0] * p->k[1] * p->k[2];
+    if (p->want_algo == PVD_ALGO_DIRECT && !direct_ok)
+        return fail(PVD_ERR_UNSUPPORTED,
+                    "direct algorithm needs zero-boundary 'same' geometry, K2 in {3,5,7}, K0,K1 <= 9 and n2 %% 4 == 0");
+    if (direct_ok && (p->want_algo == PVD_ALGO_DIRECT || (p->want_algo == PVD_ALGO_AUTO && taps <= 125))) {
+        p->algo = PVD_ALGO_DIRECT;
+        p->dbox[0] = kDirTX + p->k[0] - 1;
+        p->dbox[1] = kDirTY + p->k[1] - 1;
+        p->dbox[2] = kDirTZ + 8;  // 4 lead-in (16-byte aligned TMA start) + 64 + up to 4 right reach
+        p->dsmem = 128 + ((size_t)p->dbox[0] * p->dbox[1] * p->dbox[2] + (size_t)taps + 16) * sizeof(float) + 64;
+        p->off_taps = 0;
+        p->off_flag = align_up((size_t)taps * sizeof(float), 256);
+        p->ws_bytes = p->off_flag + 256;
+    }
+    return PVD_OK;
+}
+
+#ifndef PVD_EMULATE
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+#endif
+
+int execute_direct(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, const float* density, float rho_ref,
+                   float rho_min, float rho_cut, float scale, float* dose, cudaStream_t stream) {
+    if (T != 1) return fail(PVD_ERR_INVALID, "direct algorithm takes one activity volume: pre-accumulate with pvd_weighted_sum");
+    const float* in = h_act[0];
+    if (((uintptr_t)in & 15) || ((uintptr_t)dose & 15) || (density && ((uintptr_t)density & 15)))
+        return fail(PVD_ERR_INVALID, "direct algorithm needs 16-byte aligned volumes");
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+#ifndef PVD_EMULATE
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(PVD_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t gdim[3] = {(cuuint64_t)p->n[2], (cuuint64_t)p->n[1], (cuuint64_t)p->n[0]};  // innermost first
+    const cuuint64_t gstr[2] = {(cuuint64_t)p->n[2] * 4, (cuuint64_t)p->n[2] * p->n[1] * 4};     // bytes, dims 1..2
+    const cuuint32_t box[3] = {(cuuint32_t)p->dbox[2], (cuuint32_t)p->dbox[1], (cuuint32_t)p->dbox[0]};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PVD_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+#endif
+    DirectArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = in;
+    a.n0 = p->n[0];
+    a.n1 = p->n[1];
+    a.n2 = p->n[2];
+    a.taps = p->taps();
+    a.K0 = p->k[0];
+    a.K1 = p->k[1];
+    a.o0 = p->k[0] / 2 - (p->k[0] - 1);
+    a.o1 = p->k[1] / 2 - (p->k[1] - 1);
+    a.o2 = -4;
+    a.bx = p->dbox[0];
+    a.by = p->dbox[1];
+    a.bz = p->dbox[2];
+    a.out = dose;
+    a.density = density;
+    a.rho_ref = rho_ref;
+    a.rho_min = rho_min;
+    a.rho_cut = rho_cut;
+    a.scale = scale * (h_weights ? h_weights[0] : 1.f);
+    a.error_flag = p->flag();
+    const dim3 grid((unsigned)((p->n[2] + kDirTZ - 1) / kDirTZ), (unsigned)((p->n[1] + kDirTY - 1) / kDirTY),
+                    (unsigned)((p->n[0] + kDirTX - 1) / kDirTX));
+    p->npass = 0;
+    p->mark(stream, "D1 direct tiled conv (TMA halo tiles + density)", (density ? 12.0 : 8.0) * p->n[0] * p->n[1] * p->n[2]);
+    switch (p->k[2]) {
+        case 3: PVD_LAUNCH(direct_conv_kernel<3>, grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
+        case 5: PVD_LAUNCH(direct_conv_kernel<5>, grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
+        default: PVD_LAUNCH(direct_conv_kernel<7>, grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
+    }
+    PVD_CUDA_CHECK("direct_conv_kernel");
+    p->mark_end(stream);
     return PVD_OK;
 }
 
@@ -394,8 +490,9 @@ int pvd_good_fft_size(int n) { return good_size(n); }
 int pvd_plan_create_ex(pvd_plan** out, const int n[3], const int m[3], const int out_lo[3], const int out_n[3],
                        const int k[3], int algo) {
     if (!out || !n || !out_lo || !out_n || !k) return fail(PVD_ERR_INVALID, "null argument");
-    if (algo == PVD_ALGO_DIRECT) return fail(PVD_ERR_UNSUPPORTED, "direct algorithm not available in this build");
+    if (algo != PVD_ALGO_AUTO && algo != PVD_ALGO_FFT && algo != PVD_ALGO_DIRECT) return fail(PVD_ERR_INVALID, "unknown algo %d", algo);
     pvd_plan* p = new pvd_plan();
+    p->want_algo = algo;
     for (int i = 0; i < 3; ++i) {
         p->n[i] = n[i];
         p->k[i] = k[i];
@@ -442,8 +539,12 @@ int pvd_plan_get_info(const pvd_plan* p, pvd_plan_info* info) {
         info->k[i] = p->k[i];
     }
     info->algo = p->algo;
-    info->passes = 5;
+    info->passes = p->algo == PVD_ALGO_DIRECT ? 1 : 5;
     info->workspace_bytes = p->ws_bytes;
+    if (p->algo == PVD_ALGO_DIRECT) {
+        info->hbm_bytes_per_execute = 12.0 * p->n[0] * p->n[1] * p->n[2];
+        return PVD_OK;
+    }
     const double c = 8.0 * p->Nh;  // bytes of one half-spectrum row
     const double real_in = 4.0 * p->n[0] * p->n[1] * p->n[2];
     const double real_out = 4.0 * p->on[0] * p->on[1] * p->on[2];
@@ -469,6 +570,13 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
     cudaStream_t stream = (cudaStream_t)stream_;
     p->ws = (char*)workspace;
     p->kernel_set = false;
+    if (p->algo == PVD_ALGO_DIRECT) {
+        if (PVD_SET_SMEM(direct_conv_kernel<3>, kMaxSmem) != 0 || PVD_SET_SMEM(direct_conv_kernel<5>, kMaxSmem) != 0 ||
+            PVD_SET_SMEM(direct_conv_kernel<7>, kMaxSmem) != 0)
+            return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (direct)");
+        cudaMemsetAsync(p->flag(), 0, 256, stream);
+        return PVD_OK;
+    }
     for (int a = 0; a < 3; ++a) {
         PVD_LAUNCH(twiddle_kernel, dim3((unsigned)std::min(64, (p->m[a] + 127) / 128)), dim3(128), 0, stream, p->tw(a),
                    p->m[a]);
@@ -528,6 +636,12 @@ int pvd_plan_set_kernel(pvd_plan* p, const float* kernel, void* stream_) {
         return fail(PVD_ERR_CUDA, "finite check: stream synchronise failed");
     }
     if (bad) return fail(PVD_ERR_NONFINITE, "dose kernel contains non-finite values");
+    if (p->algo == PVD_ALGO_DIRECT) {
+        PVD_LAUNCH(flip_kernel_kernel, dim3(4), dim3(256), 0, stream, kernel, p->taps(), p->k[0], p->k[1], p->k[2]);
+        PVD_CUDA_CHECK("flip_kernel_kernel");
+        p->kernel_set = true;
+        return PVD_OK;
+    }
     const float* in[1] = {kernel};
     int rc = launch_rows_fwd(p, in, nullptr, 1, (long long)p->k[1] * p->k[2], p->k[2], p->ke, stream);
     if (rc) return rc;
@@ -549,6 +663,7 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     for (int t = 0; t < T; ++t)
         if (!h_act[t]) return fail(PVD_ERR_INVALID, "activity pointer %d is null", t);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (p->algo == PVD_ALGO_DIRECT) return execute_direct(p, h_act, h_weights, T, density, rho_ref, rho_min, rho_cut, scale, dose, stream);
     const double c = 8.0 * p->Nh;  // bytes of one half-spectrum row
     p->npass = 0;
     p->mark(stream, "P1 rows_fwd (z R2C + time-weighted sum)", 4.0 * T * p->n[0] * p->n[1] * p->n[2] + c * p->n[0] * p->n[1]);

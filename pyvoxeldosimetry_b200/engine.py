@@ -105,6 +105,10 @@ class ConvPlan:
         w = None if weights is None else [float(x) for x in weights]
         with torch.cuda.device(self.device):
             stream = _stream_ptr(self.device)
+            if self.info.algo == _capi.ALGO_DIRECT and (len(acts) > 1 or w is not None):
+                # the direct (TMA) kernel takes one volume: fold the time-weighted sum first (linearity)
+                acts = [weighted_sum(acts, w if w is not None else [1.0] * len(acts))]
+                w = None
             if len(acts) > MAX_T:  # fold the tail into one volume first (linearity)
                 if w is None:
                     w = [1.0] * len(acts)
@@ -147,8 +151,8 @@ class PlanCache:
         self._kernel_tag: Dict[tuple, object] = {}
         self._lock = threading.Lock()
 
-    def get(self, shape, kshape, boundary, device, kernel_tag, kernel_provider) -> ConvPlan:
-        key = (tuple(shape), tuple(kshape), boundary, str(device))
+    def get(self, shape, kshape, boundary, device, kernel_tag, kernel_provider, algo: int = ALGO_AUTO) -> ConvPlan:
+        key = (tuple(shape), tuple(kshape), boundary, str(device), algo)
         with self._lock:
             plan = self._plans.get(key)
             if plan is None:
@@ -156,7 +160,7 @@ class PlanCache:
                     old_key = next(iter(self._plans))
                     self._plans.pop(old_key).close()
                     self._kernel_tag.pop(old_key, None)
-                plan = ConvPlan(shape, kshape, boundary, device)
+                plan = ConvPlan(shape, kshape, boundary, device, algo)
                 self._plans[key] = plan
             if self._kernel_tag.get(key) != kernel_tag:
                 plan.set_kernel(kernel_provider())

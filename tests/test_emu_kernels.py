@@ -213,3 +213,45 @@ def test_fast_and_pipelined_kernels(lib, monkeypatch, shape, kshape, boundary, T
     if den:
         ref = orc.density_correct(ref, f(rho))
     assert orc.rel_err_of_peak(got, ref) <= TOL
+
+
+# ---- direct tiled convolution (TMA halo tiles; the box load is emulated as a zero-filled gather) ----
+@pytest.mark.parametrize("shape,kshape,den", [((9, 10, 68), (3, 3, 3), True), ((16, 8, 64), (5, 5, 5), False),
+                                              ((7, 13, 132), (5, 3, 7), True), ((3, 3, 4), (7, 9, 3), True),
+                                              ((8, 8, 8), (4, 2, 5), True)])
+def test_direct_conv_vs_oracle(lib, shape, kshape, den):
+    rng = np.random.default_rng(abs(hash((shape, kshape))) % 2**32)
+    a = rng.uniform(0, 1e3, shape)
+    k = rng.uniform(0, 1, kshape)
+    plan = lib.plan_create(shape, kshape, 1, 2)  # same boundary, PVD_ALGO_DIRECT
+    info = lib.plan_info(plan)
+    assert info.algo == 2 and info.passes == 1
+    nb = lib.plan_workspace_bytes(plan)
+    raw = np.zeros(nb + 256, np.uint8)
+    off = (-raw.ctypes.data) % 256
+    ws = raw[off:off + nb]
+    lib.plan_set_workspace(plan, ws.ctypes.data, nb)
+    k32, a32 = np.ascontiguousarray(k, np.float32), np.ascontiguousarray(a, np.float32)
+    lib.plan_set_kernel(plan, k32.ctypes.data)
+    rho = np.ascontiguousarray(rng.uniform(0.2, 2.0, shape), np.float32) if den else None
+    out = np.full(shape, np.nan, np.float32)
+    lib.conv_execute(plan, [a32.ctypes.data], None, None if rho is None else rho.ctypes.data, 1.0, 0.1, 0.3, 2.0, out.ctypes.data)
+    lib.plan_destroy(plan)
+    f = lambda x: np.asarray(x, np.float32).astype(np.float64)
+    ref = 2.0 * orc.conv_same(f(a), f(k))
+    if den:
+        ref = orc.density_correct(ref, f(rho), 1.0, 0.1, 0.3)
+    assert orc.rel_err_of_peak(out, ref) <= TOL
+
+
+def test_algo_selection(lib):
+    from pyvoxeldosimetry_b200._capi import PvdoseError
+
+    for shape, kshape, boundary, want in [((8, 8, 8), (5, 5, 5), 1, 2), ((8, 8, 8), (5, 5, 5), 0, 1), ((8, 8, 8), (7, 7, 7), 1, 1),
+                                          ((8, 8, 6), (3, 3, 3), 1, 1)]:
+        pl = lib.plan_create(shape, kshape, boundary, 0)
+        assert lib.plan_info(pl).algo == want
+        lib.plan_destroy(pl)
+    with pytest.raises(PvdoseError) as e:  # circular reference semantics cannot use TMA zero fill
+        lib.plan_create((8, 8, 8), (5, 5, 5), 0, 2)
+    assert e.value.code == -5

@@ -142,3 +142,34 @@ def test_c2_lu177_256_time_integrated(torch_cuda, boundary):
     k32 = k.astype(np.float32).astype(np.float64)
     ref = orc.conv_reference_fast(acc, k32) if boundary == "reference" else orc.conv_same(acc, k32, fast=True)
     assert orc.rel_err_of_peak(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("shape,kshape", [((64, 64, 64), (5, 5, 5)), ((40, 36, 52), (3, 3, 3)), ((33, 65, 128), (5, 3, 7)),
+                                          ((100, 96, 92), (5, 5, 5)), ((9, 7, 4), (7, 9, 3))])
+def test_direct_tma_conv_matches_oracle(torch_cuda, shape, kshape):
+    """PVD_ALGO_DIRECT: TMA-staged halo tiles, 'same' boundary; also AUTO must pick it for 5^3 and agree with FFT."""
+    from pyvoxeldosimetry_b200.engine import ConvPlan
+
+    torch = torch_cuda
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(abs(hash((shape, kshape))) % 2**32)
+    a = rng.uniform(0.0, 1e3, size=shape).astype(np.float32)
+    k = rng.uniform(0.0, 1.0, size=kshape).astype(np.float32)
+    rho = rng.choice([0.26, 1.04, 1.42], size=shape).astype(np.float32)
+    ref = orc.density_correct(orc.conv_same(a.astype(np.float64), k.astype(np.float64), fast=True), rho)
+    outs = {}
+    for name, algo in (("direct", 2), ("fft", 1)):
+        plan = ConvPlan(shape, kshape, "same", dev, algo)
+        assert plan.info.algo == algo
+        plan.set_kernel(k)
+        out = plan.execute([torch.from_numpy(a).to(dev)], None, torch.from_numpy(rho).to(dev))
+        torch.cuda.synchronize()
+        outs[name] = out.cpu().numpy()
+        plan.close()
+        assert orc.rel_err_of_peak(outs[name], ref) <= TOL, name
+    # time-weighted input through the direct path (folded by weighted_sum first)
+    plan = ConvPlan(shape, kshape, "same", dev, 2)
+    plan.set_kernel(k)
+    out = plan.execute([torch.from_numpy(a).to(dev), torch.from_numpy(a).to(dev)], [0.25, 0.5]).cpu().numpy()
+    plan.close()
+    assert orc.rel_err_of_peak(out, 0.75 * orc.conv_same(a.astype(np.float64), k.astype(np.float64), fast=True)) <= TOL

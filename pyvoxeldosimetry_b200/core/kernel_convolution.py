@@ -146,6 +146,82 @@ class KernelConvolutionCalculator(DosimetryCalculator):
             return dose
         return self._to_host(dose, out)
 
+    def calculate_dose_rate_batch(self, activity_maps: Sequence, voxel_size=None, tissue_densities=None,
+                                  outs: Optional[Sequence] = None) -> list:
+        """A1 for a batch of independent host volumes (one per patient / time point), software pipelined:
+        the H2D copy of volume i+1, the convolution of volume i and the D2H copy of volume i-1 run on three
+        CUDA streams with double-buffered device tensors, so the PCIe link (the end-to-end bottleneck: the
+        convolution itself is ~1 ms) works in both directions at once.  `tissue_densities` is None, one
+        volume shared by all, or one per activity map.  `outs`: optional host tensors/arrays to fill (pinned
+        host tensors avoid a staging copy; they may repeat, e.g. two alternating buffers)."""
+        n = len(activity_maps)
+        if n == 0:
+            return []
+        shape = tuple(activity_maps[0].shape)
+        if any(tuple(a.shape) != shape for a in activity_maps):
+            raise ValueError("All activity maps must have the same dimensions")
+        per_vol_den = isinstance(tissue_densities, (list, tuple))
+        if per_vol_den and len(tissue_densities) != n:
+            raise ValueError("need one density volume per activity map")
+        kdev, tag = self._kernel_for(voxel_size)
+        plan = self._plans.get(shape, tuple(kdev.shape), self.boundary, self.device, tag, lambda: kdev, self.algo)
+        cfg, dev = self.config, self.device
+        rr, rm, rc, sc = (float(cfg.get("rho_ref", 1.0)), float(cfg.get("rho_min", 0.1)), float(cfg.get("rho_cut", 0.0)),
+                          float(cfg.get("scale", 1.0)))
+
+        def host_f32(x):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            return t if t.dtype == torch.float32 else t.to(torch.float32)
+
+        s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        start = torch.cuda.Event()
+        start.record(torch.cuda.current_stream(dev))
+        for s in (s_in, s_cmp, s_out):
+            s.wait_event(start)
+        d_act = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        d_out = [torch.empty(plan.out_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        d_den = None
+        if tissue_densities is not None:
+            if per_vol_den:
+                d_den = [torch.empty(plan.out_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            else:
+                shared = engine.to_device_f32(tissue_densities, dev)
+                start2 = torch.cuda.Event()
+                start2.record(torch.cuda.current_stream(dev))
+                s_cmp.wait_event(start2)
+        ev_in = [torch.cuda.Event() for _ in range(n)]
+        ev_cmp = [torch.cuda.Event() for _ in range(n)]
+        ev_out = [torch.cuda.Event() for _ in range(n)]
+        results = []
+        for i in range(n):
+            slot = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_cmp[i - 2])  # device input slot free again
+                d_act[slot].copy_(host_f32(activity_maps[i]), non_blocking=True)
+                if d_den is not None:
+                    d_den[slot].copy_(host_f32(tissue_densities[i]), non_blocking=True)
+                ev_in[i].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[i])
+                if i >= 2:
+                    s_cmp.wait_event(ev_out[i - 2])  # device output slot drained
+                den = None if tissue_densities is None else (d_den[slot] if d_den is not None else shared)
+                plan.execute([d_act[slot]], None, den, rr, rm, rc, sc, out=d_out[slot])
+                ev_cmp[i].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[i])
+                if outs is not None:
+                    tgt = outs[i] if isinstance(outs[i], torch.Tensor) else torch.from_numpy(outs[i])
+                else:
+                    tgt = torch.empty(plan.out_shape, dtype=torch.float32, pin_memory=True)
+                tgt.copy_(d_out[slot], non_blocking=True)
+                ev_out[i].record(s_out)
+                results.append(tgt)
+        for s in (s_in, s_cmp, s_out):
+            s.synchronize()
+        return [r.numpy() for r in results]
+
     def calculate_absorbed_dose(self, activity_maps, time_points: List[float], voxel_size=None,
                                 tissue_densities=None, out=None):
         """A2.  time_points in hours; dose = sum_i w_i * conv(a_i, k), w = trapezoid weights * 3600."""

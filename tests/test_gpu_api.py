@@ -208,3 +208,25 @@ def test_size_independent_properties_full_c3():
     dxy = plan.execute([x, y], [2.0, -3.0])
     assert float((dxy - (2 * dx - 3 * dy)).abs().max() / dx.abs().max()) <= TOL
     plan.close()
+
+
+def test_pipelined_batch_api_matches_single_calls():
+    import torch
+
+    from pyvoxeldosimetry_b200 import KernelConvolutionCalculator
+
+    rng = np.random.default_rng(9)
+    shape = (48, 40, 64)
+    calc = KernelConvolutionCalculator("Y90", "water", 1.0, config={"kernel_grid": (9, 9, 9), "boundary": "same"})
+    vols = [rng.uniform(0, 1e3, shape).astype(np.float32) for _ in range(5)]
+    dens = [rng.choice([0.26, 1.04, 1.42], size=shape).astype(np.float32) for _ in range(5)]
+    got = calc.calculate_dose_rate_batch(vols, (1.0, 1.0, 1.0), dens)
+    for v, d, g in zip(vols, dens, got):
+        ref = calc.calculate_dose_rate(v, (1.0, 1.0, 1.0), tissue_densities=d)
+        assert np.array_equal(g, ref)
+    shared = calc.calculate_dose_rate_batch(vols[:3], (1.0, 1.0, 1.0), dens[0])
+    assert np.array_equal(shared[1], calc.calculate_dose_rate(vols[1], (1.0, 1.0, 1.0), tissue_densities=dens[0]))
+    outs = [torch.empty(shape).pin_memory() for _ in range(3)]
+    r = calc.calculate_dose_rate_batch(vols[:3], (1.0, 1.0, 1.0), None, outs)
+    assert orc.rel_err_of_peak(r[2], orc.conv_same(f64(vols[2]), f64(calc.kernel))) <= TOL
+    assert calc.calculate_dose_rate_batch([], (1.0, 1.0, 1.0)) == []

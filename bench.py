@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the kernel-convolution dose path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1] [--boundary reference|same]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1|c4|c5] [--boundary reference|same]
 
 A *step* is one pass of the hot path over one synthetic patient volume per GPU:
   workload c3 (default, the configuration the metric is quoted on): 512x512x400 float32 activity,
@@ -37,6 +37,11 @@ WORKLOADS = {
                desc="C2: Lu-177 4-timepoint time-integrated dose 256^3, 31^3 DVK @4.8mm"),
     "c1": dict(shape=(48, 48, 48), kgrid=(64, 64, 64), nuclide="Y90", voxel=1.0, T=1, density=False,
                desc="C1: examples/single_timepoint_y90_physical_decay.py 48^3, 64^3 DVK"),
+    # multi-GPU configurations (strong scaling: the job is fixed, ranks share it)
+    "c4": dict(shape=(256, 256, 256), kgrid=(31, 31, 31), nuclide="Lu177", voxel=4.8, T=4, density=False, volumes=64,
+               desc="C4: 64 patient volumes (256^3, 4 time points, 31^3 DVK) sharded over the ranks"),
+    "c5": dict(shape=(1024, 1024, 800), kgrid=(51, 51, 51), nuclide="Y90", voxel=1.0, T=1, density=True,
+               desc="C5: 1024x1024x800 volume, 51^3 DVK, slabs along axis 0 + kernel-radius halo exchange (NCCL send/recv)"),
 }
 
 
@@ -156,13 +161,27 @@ def cpu_reference_time(wl, budget_s: float, acts, rho, kernel64):
         if np.prod(c) / rate * 1.6 <= budget_s:
             pick = c
             break
-    a = np.ascontiguousarray(acts[0][: pick[0], : pick[1], : pick[2]]).astype(np.float64)
+    subs = [np.ascontiguousarray(m[: pick[0], : pick[1], : pick[2]]).astype(np.float64) for m in acts]
     t0 = time.perf_counter()
-    d = orc.conv_reference(a, kernel64)
-    if rho is not None:
-        d = orc.density_correct(d, rho[: pick[0], : pick[1], : pick[2]])
+    d = reference_step(subs, kernel64, None if rho is None else rho[: pick[0], : pick[1], : pick[2]])
     dt = time.perf_counter() - t0
-    return a.size / dt, f"literal np.fft.ifftn(fftn(a)*fftn(k,a.shape)).real float64 on a {pick[0]}x{pick[1]}x{pick[2]} sub-volume", dt
+    what = "literal np.fft.ifftn(fftn(a)*fftn(k,a.shape)).real float64" if len(acts) == 1 else \
+        f"literal calculate_absorbed_dose loop: {len(acts)} np.fft convolutions + trapezoid (core/kernel_convolution.py:94-106)"
+    return subs[0].size / dt, f"{what} on a {pick[0]}x{pick[1]}x{pick[2]} sub-volume", dt
+
+
+def reference_step(maps64, kernel64, rho):
+    """One unit of the reference's work for the workload: T = 1 -> calculate_dose_rate, T > 1 -> the literal
+    calculate_absorbed_dose loop (one FFT convolution per time point, kernel FFT recomputed every time)."""
+    from oracle import dose_oracle as orc
+
+    if len(maps64) == 1:
+        d = orc.conv_reference(maps64[0], kernel64)
+    else:
+        d = orc.absorbed_dose_trapezoid(maps64, [4.0, 24.0, 96.0, 168.0][: len(maps64)], kernel64)
+    if rho is not None:
+        d = orc.density_correct(d, rho)
+    return d
 
 
 def run_reference(args, wl):
@@ -178,15 +197,14 @@ def run_reference(args, wl):
     per = total_budget / max(1, args.steps + args.warmup)
     rate, sample, dt = cpu_reference_time(wl, per, acts, rho, k64)  # also serves as warm-up / calibration
     pick = tuple(int(x) for x in sample.split(" on a ")[1].split(" ")[0].split("x"))
-    a = np.ascontiguousarray(acts[0][: pick[0], : pick[1], : pick[2]]).astype(np.float64)
+    subs = [np.ascontiguousarray(m[: pick[0], : pick[1], : pick[2]]).astype(np.float64) for m in acts]
+    a = subs[0]
     r = None if rho is None else rho[: pick[0], : pick[1], : pick[2]]
     for _ in range(max(0, args.warmup - 1)):
-        orc.conv_reference(a, k64)
+        reference_step(subs, k64, r)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        d = orc.conv_reference(a, k64)
-        if r is not None:
-            d = orc.density_correct(d, r)
+        reference_step(subs, k64, r)
     dt = (time.perf_counter() - t0) / args.steps
     vps = a.size / dt
     value = vps / nvox
@@ -365,6 +383,85 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def run_sharded(args, wl, name):
+    """C4 / C5: a fixed job shared by the ranks (strong scaling).  C4 shards independent volumes (no collective);
+    C5 splits one volume into slabs and exchanges kernel-radius halos between neighbours with NCCL send/recv."""
+    import torch
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    else:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group(backend="nccl", rank=0, world_size=1, device_id=dev)
+    from pyvoxeldosimetry_b200 import KernelConvolutionCalculator
+    from pyvoxeldosimetry_b200.engine import ConvPlan
+    from pyvoxeldosimetry_b200.multi_gpu import SlabConvolver, shard_range
+
+    boundary = args.boundary if name == "c4" else "same"
+    calc = KernelConvolutionCalculator(wl["nuclide"], "water", wl["voxel"], config={"kernel_grid": wl["kgrid"], "boundary": boundary, "device": str(dev)})
+    kdev = calc._kernel_dev
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    if name == "c4":
+        from pyvoxeldosimetry_b200.core import trapezoid_weights
+
+        mine = shard_range(wl["volumes"], world, rank)
+        plan = ConvPlan(wl["shape"], wl["kgrid"], boundary, dev)
+        plan.set_kernel(kdev)
+        sets = [[torch.rand(wl["shape"], device=dev, generator=g) for _ in range(wl["T"])] for _ in range(2)]  # two patients' buffers, alternated
+        w = trapezoid_weights([4.0, 24.0, 96.0, 168.0], 3600.0)
+        out = torch.empty(plan.out_shape, device=dev)
+
+        def step():
+            for v in mine:
+                plan.execute(sets[v & 1], w, None, out=out)
+        units, extra, launches = wl["volumes"], {"volumes_per_rank": len(mine), "fft_shape": list(plan.fft_shape)}, 5 * len(mine)
+    else:
+        sc = SlabConvolver(wl["shape"], kdev, boundary, device=dev)
+        local_in = torch.rand((sc.hi - sc.lo,) + tuple(wl["shape"][1:]), device=dev, generator=g)
+        rho = torch.rand((sc.hi - sc.lo,) + tuple(wl["shape"][1:]), device=dev, generator=g) + 0.5
+
+        def step():
+            sc(local_in, rho)
+        units, launches = 1, 5
+        extra = {"slab_planes": sc.hi - sc.lo, "halo_planes": sc.geom["n"][0] - (sc.hi - sc.lo), "local_fft_shape": list(sc.plan.fft_shape)}
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    if rank == 0:
+        nvox = float(np.prod(wl["shape"]))
+        value = units * 1e3 / ms_step
+        alg = 4.0 * (wl["T"] + 1 + (1 if wl["density"] else 0)) * nvox * units
+        peak_gbs, peak_src = peaks()
+        print(json.dumps({
+            "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox, "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict({"workload": wl["desc"], "boundary": boundary, "l2": "inputs exceed the 126 MB L2"}, **extra),
+            "roofline": {"bound": "hbm", "achieved": round(alg / (ms_step * 1e-3) / 1e9, 1), "peak": peak_gbs * world, "unit": "GB/s",
+                         "frac": round(alg / (ms_step * 1e-3) / 1e9 / (peak_gbs * world), 4), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
+            "gpu_launches": launches * args.steps,
+        }), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,6 +475,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif args.workload in ("c4", "c5"):
+        run_sharded(args, wl, args.workload)
     else:
         run_ours(args, wl)
 

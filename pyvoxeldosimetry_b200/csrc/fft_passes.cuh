@@ -152,6 +152,7 @@ struct RowInvArgs {
     float rho_ref, rho_min, rho_cut, scale;
     int M2, Nh;
     int Llog;
+    int den_ldg;  // pipelined kernel: 1 = density via LDG in the store phase, 0 = staged through shared memory
     const float2* tw;
     Stages st;
 };

@@ -211,13 +211,21 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
             }
         }
         __syncthreads();  // staging buffer consumed
-        if (has_den) issue_density(t);
+        const int tn = t + gridDim.x;
+        // den_ldg: density comes through batched LDGs in the store phase, so the staging buffer is free NOW and
+        // the next tile's spectrum rows stream in during the inverse FFT and the stores.  Otherwise the density
+        // rows of this tile are staged here and the next tile is requested only after the store phase.
+        if (g.den_ldg) {
+            if (tn < ntiles) issue_spec(tn);
+        } else if (has_den) {
+            issue_density(t);
+        }
         cp_async_commit();
         auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
         auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
         fast_fft<N, W, LS, NT, +1, R1, R2, R3, true, true>(sm_in, sm_out, tile, tws);
-        cp_async_wait<0>();
-        __syncthreads();  // transform done, density rows landed
+        if (!g.den_ldg) cp_async_wait<0>();
+        __syncthreads();  // transform done (and staged density rows landed)
         const int row0 = t * 32;
         const float* Zf = reinterpret_cast<const float*>(tile);
         for (int rr = warp; rr < 32; rr += NWARPS) {
@@ -226,25 +234,44 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
             const int x = R / O1, y = R - x * O1;
             float* __restrict__ dst = g.out + x * g.out_s0 + y * g.out_s1;
             const float* srcf = Zf + (rr >> 1) * 2 + (rr & 1) + (size_t)z_lo * (2 * LS);
-            const float* den = rawf + rr * LSF;
             constexpr int ZIT = (N + 31) / 32;
-            PVD_UNROLL
-            for (int i = 0; i < ZIT; ++i) {
-                const int z = lane + 32 * i;
-                if (z < O2) {
-                    float v = srcf[z * (2 * LS)] * scale;
-                    if (has_den) {
-                        const float rho = den[z];
-                        v = (rho < rho_cut) ? 0.f : v * __fdividef(rho_ref, fmaxf(rho, rho_min));
+            if (has_den && g.den_ldg) {
+                const float* __restrict__ dg = g.density + x * g.den_s0 + y * g.den_s1;
+                float rho[ZIT];
+                PVD_UNROLL
+                for (int i = 0; i < ZIT; ++i) {
+                    const int z = lane + 32 * i;
+                    rho[i] = (z < O2) ? __ldg(dg + z) : 1.f;
+                }
+                PVD_UNROLL
+                for (int i = 0; i < ZIT; ++i) {
+                    const int z = lane + 32 * i;
+                    if (z < O2) {
+                        const float v = srcf[z * (2 * LS)] * scale;
+                        dst[z] = (rho[i] < rho_cut) ? 0.f : v * __fdividef(rho_ref, fmaxf(rho[i], rho_min));
                     }
-                    dst[z] = v;
+                }
+            } else {
+                const float* den = rawf + rr * LSF;
+                PVD_UNROLL
+                for (int i = 0; i < ZIT; ++i) {
+                    const int z = lane + 32 * i;
+                    if (z < O2) {
+                        float v = srcf[z * (2 * LS)] * scale;
+                        if (has_den) {
+                            const float rho = den[z];
+                            v = (rho < rho_cut) ? 0.f : v * __fdividef(rho_ref, fmaxf(rho, rho_min));
+                        }
+                        dst[z] = v;
+                    }
                 }
             }
         }
-        __syncthreads();  // staging buffer (density) and tile free again
-        const int tn = t + gridDim.x;
-        if (tn < ntiles) issue_spec(tn);
-        cp_async_commit();
+        if (!g.den_ldg) {
+            __syncthreads();  // staging buffer (density) and tile free again
+            if (tn < ntiles) issue_spec(tn);
+            cp_async_commit();
+        }
     }
     cp_async_wait<0>();
 }

@@ -728,6 +728,10 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     a.Llog = p->rowLlog;
     a.tw = p->tw(2);
     a.st = p->st[2];
+    {
+        const char* e = getenv("PVD_P5_DEN_STAGED");
+        a.den_ldg = (e && e[0] == '1') ? 0 : 1;
+    }
     const long long nrows = (long long)p->on[0] * p->on[1];
     const long long per = 2LL << p->rowLlog;
     if (p->fastRows && p->usePipe && p->rowPipeGrid[1] > 0 && nrows < 2000000000LL &&

@@ -279,11 +279,24 @@ __global__ void __launch_bounds__(NT) rows_fwd_fast_kernel(const RowFwdArgs g) {
             PVD_UNROLL
             for (int z = lane; z < N; z += 32) dstf[z * (2 * LS)] = (valid && z < n2) ? w0 * __ldg(p0 + z) : 0.f;
         } else {
-            for (int z = lane; z < N; z += 32) {
-                float v = 0.f;
-                if (valid && z < n2)
-                    for (int t = 0; t < T; ++t) v += g.w[t] * __ldg(g.in[t] + off + z);
-                dstf[z * (2 * LS)] = v;
+            // time-weighted sum: one batch of independent loads per time point (memory-level parallelism)
+            constexpr int ZIT = (N + 31) / 32;
+            float acc[ZIT];
+            PVD_UNROLL
+            for (int i = 0; i < ZIT; ++i) acc[i] = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const float* __restrict__ pt = g.in[t] + off;
+                const float wt = g.w[t];
+                PVD_UNROLL
+                for (int i = 0; i < ZIT; ++i) {
+                    const int z = lane + 32 * i;
+                    if (valid && z < n2) acc[i] = fmaf(wt, __ldg(pt + z), acc[i]);
+                }
+            }
+            PVD_UNROLL
+            for (int i = 0; i < ZIT; ++i) {
+                const int z = lane + 32 * i;
+                if (z < N) dstf[z * (2 * LS)] = acc[i];
             }
         }
     }

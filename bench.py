@@ -355,6 +355,10 @@ def run_ours(args, wl):
         ksum = sum(k["ms"] for k in kernels) or ms_step
         dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        traffic = None  # dram__bytes_read+write of the whole path from the committed ncu --set full capture (same workload only)
+        tpath = os.path.join(REPO, "profiles", "r01_dram_traffic_c3.json")
+        if args.workload == "c3" and args.boundary == "reference" and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("_whole_path_dram_bytes")
         line = {
             "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox,
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
@@ -363,7 +367,7 @@ def run_ours(args, wl):
                        "volumes_per_step_per_gpu": 1, "l2": "inputs (>=419 MB per volume for c3) exceed the 126 MB L2",
                        "parallelism": f"independent volumes sharded over {world} rank(s), no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
-                         "frac": round(achieved / peak_gbs, 4), "traffic": None,
+                         "frac": round(achieved / peak_gbs, 4), "traffic": traffic,
                          "what": "whole conv path (all launches of one volume): algorithmic 4*(T+1+[density]) B/voxel / time per volume",
                          "peak_source": peak_src, "algorithmic_bytes_per_volume": alg_bytes,
                          "implementation_bytes_per_volume": info.hbm_bytes_per_execute,

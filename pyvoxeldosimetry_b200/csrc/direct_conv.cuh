@@ -65,7 +65,8 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 }
 #endif
 
-template <int KZ>
+// KX > 0: cubic fast path with K0 == KX known at compile time; KX == 0: any K0 <= 9 (runtime loop).
+template <int KZ, int KX>
 __global__ void __launch_bounds__(kDirThreads) direct_conv_kernel(const __grid_constant__ CUtensorMap tmap, const DirectArgs g) {
     // The TMA box must start on a 16-byte boundary along z (measured: a misaligned innermost coordinate
     // raises "illegal instruction", scripts/tma_probe), so the box starts at z0 - 4 and the taps index
@@ -120,6 +121,44 @@ __global__ void __launch_bounds__(kDirThreads) direct_conv_kernel(const __grid_c
         for (int z = 0; z < 4; ++z) acc[x][z] = 0.f;
     }
     const int rowstride = g.bz, planestride = g.by * g.bz;
+    if constexpr (KX > 0) {
+        // Cubic-kernel fast path (K0 == KX compile time): per ky the KX*KZ taps sit in registers and each of
+        // the 4+KX-1 input rows this thread needs is loaded ONCE (3 x LDS.128) and reused by all four x
+        // outputs - 2.5x fewer shared-memory loads than the generic loop below (ncu: that one is l1tex-bound).
+        for (int ky = 0; ky < g.K1; ++ky) {
+            float t[KX][KZ];
+            PVD_UNROLL
+            for (int kx = 0; kx < KX; ++kx) {
+                PVD_UNROLL
+                for (int kz = 0; kz < KZ; ++kz) t[kx][kz] = taps[(kx * g.K1 + ky) * KZ + kz];
+            }
+            const float* rowbase = tile + (xh * 4) * planestride + (y + ky) * rowstride + 4 * zq;
+            PVD_UNROLL
+            for (int r = 0; r < 4 + KX - 1; ++r) {
+                float rr[RL * 4];
+                const float4* rp = reinterpret_cast<const float4*>(rowbase + r * planestride);
+                PVD_UNROLL
+                for (int i = 0; i < RL; ++i) {
+                    const float4 v = rp[i];
+                    rr[4 * i] = v.x;
+                    rr[4 * i + 1] = v.y;
+                    rr[4 * i + 2] = v.z;
+                    rr[4 * i + 3] = v.w;
+                }
+                PVD_UNROLL
+                for (int x = 0; x < 4; ++x) {
+                    const int kx = r - x;  // compile time after unrolling
+                    if (kx >= 0 && kx < KX) {
+                        PVD_UNROLL
+                        for (int kz = 0; kz < KZ; ++kz) {
+                            PVD_UNROLL
+                            for (int z = 0; z < 4; ++z) acc[x][z] = fmaf(t[kx][kz], rr[z + kz + ZS], acc[x][z]);
+                        }
+                    }
+                }
+            }
+        }
+    } else
     for (int kx = 0; kx < g.K0; ++kx) {
         for (int ky = 0; ky < g.K1; ++ky) {
             float t[KZ];

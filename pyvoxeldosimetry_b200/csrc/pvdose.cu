@@ -491,10 +491,20 @@ int execute_direct(pvd_plan* p, const float* const* h_act, const float* h_weight
                     (unsigned)((p->n[0] + kDirTX - 1) / kDirTX));
     p->npass = 0;
     p->mark(stream, "D1 direct tiled conv (TMA halo tiles + density)", (density ? 12.0 : 8.0) * p->n[0] * p->n[1] * p->n[2]);
+    const bool cubic = p->k[0] == p->k[2];  // K0 == K2: register-resident taps, each input row loaded once
     switch (p->k[2]) {
-        case 3: PVD_LAUNCH(direct_conv_kernel<3>, grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
-        case 5: PVD_LAUNCH(direct_conv_kernel<5>, grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
-        default: PVD_LAUNCH(direct_conv_kernel<7>, grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
+        case 3:
+            if (cubic) PVD_LAUNCH((direct_conv_kernel<3, 3>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
+            else PVD_LAUNCH((direct_conv_kernel<3, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
+            break;
+        case 5:
+            if (cubic) PVD_LAUNCH((direct_conv_kernel<5, 5>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
+            else PVD_LAUNCH((direct_conv_kernel<5, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
+            break;
+        default:
+            if (cubic) PVD_LAUNCH((direct_conv_kernel<7, 7>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
+            else PVD_LAUNCH((direct_conv_kernel<7, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
+            break;
     }
     PVD_CUDA_CHECK("direct_conv_kernel");
     p->mark_end(stream);
@@ -593,8 +603,9 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
     p->ws = (char*)workspace;
     p->kernel_set = false;
     if (p->algo == PVD_ALGO_DIRECT) {
-        if (PVD_SET_SMEM(direct_conv_kernel<3>, kMaxSmem) != 0 || PVD_SET_SMEM(direct_conv_kernel<5>, kMaxSmem) != 0 ||
-            PVD_SET_SMEM(direct_conv_kernel<7>, kMaxSmem) != 0)
+        if (PVD_SET_SMEM((direct_conv_kernel<3, 0>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_kernel<5, 0>), kMaxSmem) != 0 ||
+            PVD_SET_SMEM((direct_conv_kernel<7, 0>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_kernel<3, 3>), kMaxSmem) != 0 ||
+            PVD_SET_SMEM((direct_conv_kernel<5, 5>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_kernel<7, 7>), kMaxSmem) != 0)
             return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (direct)");
         cudaMemsetAsync(p->flag(), 0, 256, stream);
         return PVD_OK;

@@ -28,6 +28,9 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+# NCCL prints its version banner on STDOUT when NCCL_DEBUG is VERSION/INFO: stdout carries exactly ONE JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+    os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
 
 WORKLOADS = {
     # name: (shape, kernel grid, nuclide, voxel mm, T, density)

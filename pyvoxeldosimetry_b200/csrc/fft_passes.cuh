@@ -152,7 +152,7 @@ struct RowInvArgs {
     float rho_ref, rho_min, rho_cut, scale;
     int M2, Nh;
     int Llog;
-    int den_ldg;  // pipelined kernel: 1 = density via LDG in the store phase, 0 = staged through shared memory
+    int vec4;  // pipelined kernel: dose/density rows are 16-byte aligned and O2 % 4 == 0 -> 128-bit store phase
     const float2* tw;
     Stages st;
 };

@@ -56,14 +56,24 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
     const float* __restrict__ in0 = g.in[0];
     const float w0 = g.w[0];
     const int n1 = g.n1, n2b = g.n2 * 4;
+    // (x, y) of a tile row from the tile's first row: one division per tile instead of one per row
+    auto row_xy = [&](int x0, int y0, int rr, int& x, int& y) {
+        x = x0;
+        y = y0 + rr;
+        while (y >= n1) {
+            y -= n1;
+            ++x;
+        }
+    };
     auto issue = [&](int t) {  // one warp per row: the row address is warp-uniform, lanes walk the 16-byte chunks
         const int row0 = t * 32;
+        const int x0 = row0 / n1, y0 = row0 - x0 * n1;
         for (int rr = warp; rr < 32; rr += NWARPS) {
-            const int R = row0 + rr;
-            const bool valid = R < (int)nrows;
+            const bool valid = row0 + rr < (int)nrows;
             long long off = 0;
             if (valid) {
-                const int x = R / n1, y = R - x * n1;
+                int x, y;
+                row_xy(x0, y0, rr, x, y);
                 off = x * g.in_s0 + y * g.in_s1;
             }
             const float* src = in0 + off;
@@ -79,8 +89,10 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
     if (t < ntiles) issue(t);
     cp_async_commit();
     const int wl = threadIdx.x % W;
-    const float* rawA = raw + (2 * wl) * LSF;
-    const float* rawB = rawA + LSF;
+    // line wl packs staged rows wl (re) and wl + 16 (im): row starts are then 20 (mod 32) banks apart for
+    // LSF = 404, i.e. 2-way conflicts over the 16 lines of a warp (adjacent rows 2wl, 2wl+1 gave 4-way)
+    const float* rawA = raw + wl * LSF;
+    const float* rawB = rawA + W * LSF;
     for (; t < ntiles; t += gridDim.x) {
         cp_async_wait<0>();
         __syncthreads();  // staged rows of tile t visible; previous tile's split phase finished with `tile`
@@ -102,14 +114,15 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
         __syncthreads();
         // Hermitian split: A[k] = (Z[k] + conj(Z[N-k]))/2, B[k] = (Z[k] - conj(Z[N-k]))/(2i)
         const int row0 = t * 32;
+        const int x0 = row0 / n1, y0 = row0 - x0 * n1;
         const int Nh = g.Nh;
         for (int rr = warp; rr < 32; rr += NWARPS) {
-            const int R = row0 + rr;
-            if (R >= (int)nrows) continue;
-            const int x = R / n1, y = R - x * n1;
+            if (row0 + rr >= (int)nrows) continue;
+            int x, y;
+            row_xy(x0, y0, rr, x, y);
             float2* __restrict__ dst = g.out + x * g.out_s0 + y * g.out_s1;
-            const int line = rr >> 1;
-            const bool odd = rr & 1;
+            const int line = rr & (W - 1);
+            const bool odd = rr >= W;
             constexpr int KIT = (N / 2 + 1 + 31) / 32;
             PVD_UNROLL
             for (int i = 0; i < KIT; ++i) {
@@ -126,15 +139,42 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
     cp_async_wait<0>();
 }
 
+// 128-bit global accesses of the store phase (density rows are read once, dose rows written once)
+#ifdef PVD_EMULATE
+static inline float4 ldg128_ro(const float* p) { return *reinterpret_cast<const float4*>(p); }
+static inline void stg128(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+#else
+__device__ __forceinline__ float4 ldg128_ro(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg128(float* p, float4 v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+#endif
+
+// dose = v * sr / max(rho, rho_min), zero below rho_cut   (sr = scale * rho_ref)
+__device__ __forceinline__ float den_apply(float v, float rho, float sr, float rho_min, float rho_cut) {
+    const float f = v * __fdividef(sr, fmaxf(rho, rho_min));
+    return (rho < rho_cut) ? 0.f : f;
+}
+
+// P5.  The last radix stage does not return to the [index][line] exchange layout: it writes the two real rows
+// of every line ROW-MAJOR (and already cropped: index - z_lo) over the tile, so the store phase is a straight
+// copy with 128-bit shared loads, 128-bit density loads and 128-bit dose stores - a quarter of the memory
+// instructions and guards of the element-wise version.  Row r of the tile pairs with row r + 16 in one line.
 template <int N, int NT, int MINB, int R1, int R2, int R3>
 __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArgs g) {
     constexpr int W = 16, LS = 17;
     using RS = RowStage<N>;
-    constexpr int LSF = RS::LSF, LSC = RS::LSC, CHR = RS::CHR, CHC = RS::CHC;
+    constexpr int LSC = RS::LSC, CHC = RS::CHC;
+    constexpr int LSA = RS::LSF;  // floats per row of the row-major result (16-byte multiple, 32 rows fit the tile)
+    static_assert(32 * LSA * 4 <= N * LS * 8, "row-major result must fit the exchange tile");
     PVD_DYN_SMEM(float2, smem);
     float2* tile = smem;
-    float2* rawc = smem + N * LS;                       // staged complex rows, later the density rows
-    float* rawf = reinterpret_cast<float*>(rawc);
+    float* rowbuf = reinterpret_cast<float*>(smem);
+    float2* rawc = smem + N * LS;  // staged complex rows
     float2* tws = rawc + 32 * LSC;
     Sched<N, R1, R2, R3>::build(tws, g.tw);
     const long long nrows = (long long)g.O0 * g.O1;
@@ -143,14 +183,25 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
     constexpr int NWARPS = NT / 32;
     const int Nh = g.Nh, O1 = g.O1, O2 = g.O2, z_lo = g.z_lo;
     const bool has_den = g.density != nullptr;
+    const bool vec4 = g.vec4 != 0;
+    // (x, y) of a tile row from the tile's first row: one division per tile instead of one per row
+    auto row_xy = [&](int x0, int y0, int rr, int& x, int& y) {
+        x = x0;
+        y = y0 + rr;
+        while (y >= O1) {
+            y -= O1;
+            ++x;
+        }
+    };
     auto issue_spec = [&](int t) {
         const int row0 = t * 32;
+        const int x0 = row0 / O1, y0 = row0 - x0 * O1;
         for (int rr = warp; rr < 32; rr += NWARPS) {
-            const int R = row0 + rr;
-            const bool valid = R < (int)nrows;
+            const bool valid = row0 + rr < (int)nrows;
             long long off = 0;
             if (valid) {
-                const int x = R / O1, y = R - x * O1;
+                int x, y;
+                row_xy(x0, y0, rr, x, y);
                 off = (x + g.x_lo) * g.in_s0 + (y + g.y_lo) * g.in_s1;
             }
             const float2* src = g.in + off;
@@ -162,37 +213,18 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
             }
         }
     };
-    auto issue_density = [&](int t) {
-        const int row0 = t * 32;
-        const int o2b = O2 * 4;
-        for (int rr = warp; rr < 32; rr += NWARPS) {
-            const int R = row0 + rr;
-            const bool valid = R < (int)nrows;
-            long long off = 0;
-            if (valid) {
-                const int x = R / O1, y = R - x * O1;
-                off = x * g.den_s0 + y * g.den_s1;
-            }
-            const float* src = g.density + off;
-            float* dstp = rawf + rr * LSF;
-            PVD_UNROLL
-            for (int i = 0; i < (CHR + 31) / 32; ++i) {
-                const int ch = lane + 32 * i;
-                if (ch < CHR) cp_async16_partial(dstp + ch * 4, src + ch * 4, valid ? o2b - ch * 16 : 0);
-            }
-        }
-    };
     int t = blockIdx.x;
     if (t < ntiles) issue_spec(t);
     cp_async_commit();
-    const float scale = g.scale, rho_ref = g.rho_ref, rho_min = g.rho_min, rho_cut = g.rho_cut;
+    const float sr = g.scale * (has_den ? g.rho_ref : 1.f), rho_min = g.rho_min, rho_cut = g.rho_cut;
+    const int wl = threadIdx.x % W;
     for (; t < ntiles; t += gridDim.x) {
         cp_async_wait<0>();
-        __syncthreads();
+        __syncthreads();  // staged rows landed; the previous tile's store phase is done with the tile
         // rebuild the packed Hermitian line Z = A + i*B for each pair of rows (lanes along k)
         for (int line = warp; line < W; line += NWARPS) {
-            const float2* pa = rawc + (2 * line) * LSC;
-            const float2* pb = pa + LSC;
+            const float2* pa = rawc + line * LSC;
+            const float2* pb = pa + W * LSC;
             constexpr int KIT = (N / 2 + 1 + 31) / 32;
             PVD_UNROLL
             for (int i = 0; i < KIT; ++i) {
@@ -210,67 +242,69 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
                 }
             }
         }
-        __syncthreads();  // staging buffer consumed
+        __syncthreads();  // staging buffer consumed: the next tile's spectrum rows stream in during the FFT and the stores
         const int tn = t + gridDim.x;
-        // den_ldg: density comes through batched LDGs in the store phase, so the staging buffer is free NOW and
-        // the next tile's spectrum rows stream in during the inverse FFT and the stores.  Otherwise the density
-        // rows of this tile are staged here and the next tile is requested only after the store phase.
-        if (g.den_ldg) {
-            if (tn < ntiles) issue_spec(tn);
-        } else if (has_den) {
-            issue_density(t);
-        }
+        if (tn < ntiles) issue_spec(tn);
         cp_async_commit();
         auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
-        auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
-        fast_fft<N, W, LS, NT, +1, R1, R2, R3, true, true>(sm_in, sm_out, tile, tws);
-        if (!g.den_ldg) cp_async_wait<0>();
-        __syncthreads();  // transform done (and staged density rows landed)
+        float* rowA = rowbuf + wl * LSA - z_lo;
+        auto row_out = [&](int, int, int idx, int, float2 v) {
+            if ((unsigned)(idx - z_lo) < (unsigned)O2) {
+                rowA[idx] = v.x;
+                rowA[idx + W * LSA] = v.y;
+            }
+        };
+        fast_fft<N, W, LS, NT, +1, R1, R2, R3, true, true>(sm_in, row_out, tile, tws);
+        __syncthreads();  // all rows complete
         const int row0 = t * 32;
-        const float* Zf = reinterpret_cast<const float*>(tile);
+        const int x0 = row0 / O1, y0 = row0 - x0 * O1;
         for (int rr = warp; rr < 32; rr += NWARPS) {
-            const int R = row0 + rr;
-            if (R >= (int)nrows) continue;
-            const int x = R / O1, y = R - x * O1;
+            if (row0 + rr >= (int)nrows) continue;
+            int x, y;
+            row_xy(x0, y0, rr, x, y);
             float* __restrict__ dst = g.out + x * g.out_s0 + y * g.out_s1;
-            const float* srcf = Zf + (rr >> 1) * 2 + (rr & 1) + (size_t)z_lo * (2 * LS);
-            constexpr int ZIT = (N + 31) / 32;
-            if (has_den && g.den_ldg) {
-                const float* __restrict__ dg = g.density + x * g.den_s0 + y * g.den_s1;
-                float rho[ZIT];
+            const float* __restrict__ dg = has_den ? g.density + x * g.den_s0 + y * g.den_s1 : nullptr;
+            const float* srow = rowbuf + rr * LSA;
+            if (vec4 && has_den) {
+                constexpr int QIT = ((N + 3) / 4 + 31) / 32;
+                float4 rho[QIT];
                 PVD_UNROLL
-                for (int i = 0; i < ZIT; ++i) {
-                    const int z = lane + 32 * i;
-                    rho[i] = (z < O2) ? __ldg(dg + z) : 1.f;
+                for (int i = 0; i < QIT; ++i) {
+                    const int z = 4 * (lane + 32 * i);
+                    rho[i] = (z < O2) ? ldg128_ro(dg + z) : make_float4(1.f, 1.f, 1.f, 1.f);
                 }
                 PVD_UNROLL
-                for (int i = 0; i < ZIT; ++i) {
-                    const int z = lane + 32 * i;
+                for (int i = 0; i < QIT; ++i) {
+                    const int z = 4 * (lane + 32 * i);
+                    float4 v = *reinterpret_cast<const float4*>(srow + (z < O2 ? z : 0));
+                    v.x = den_apply(v.x, rho[i].x, sr, rho_min, rho_cut);
+                    v.y = den_apply(v.y, rho[i].y, sr, rho_min, rho_cut);
+                    v.z = den_apply(v.z, rho[i].z, sr, rho_min, rho_cut);
+                    v.w = den_apply(v.w, rho[i].w, sr, rho_min, rho_cut);
+                    if (z < O2) stg128(dst + z, v);
+                }
+            } else if (vec4) {
+                constexpr int QIT = ((N + 3) / 4 + 31) / 32;
+                PVD_UNROLL
+                for (int i = 0; i < QIT; ++i) {
+                    const int z = 4 * (lane + 32 * i);
                     if (z < O2) {
-                        const float v = srcf[z * (2 * LS)] * scale;
-                        dst[z] = (rho[i] < rho_cut) ? 0.f : v * __fdividef(rho_ref, fmaxf(rho[i], rho_min));
+                        float4 v = *reinterpret_cast<const float4*>(srow + z);
+                        v.x *= sr;
+                        v.y *= sr;
+                        v.z *= sr;
+                        v.w *= sr;
+                        stg128(dst + z, v);
                     }
                 }
             } else {
-                const float* den = rawf + rr * LSF;
+                constexpr int ZIT = (N + 31) / 32;
                 PVD_UNROLL
                 for (int i = 0; i < ZIT; ++i) {
                     const int z = lane + 32 * i;
-                    if (z < O2) {
-                        float v = srcf[z * (2 * LS)] * scale;
-                        if (has_den) {
-                            const float rho = den[z];
-                            v = (rho < rho_cut) ? 0.f : v * __fdividef(rho_ref, fmaxf(rho, rho_min));
-                        }
-                        dst[z] = v;
-                    }
+                    if (z < O2) dst[z] = has_den ? den_apply(srow[z], __ldg(dg + z), sr, rho_min, rho_cut) : srow[z] * sr;
                 }
             }
-        }
-        if (!g.den_ldg) {
-            __syncthreads();  // staging buffer (density) and tile free again
-            if (tn < ntiles) issue_spec(tn);
-            cp_async_commit();
         }
     }
     cp_async_wait<0>();

@@ -739,14 +739,13 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     a.Llog = p->rowLlog;
     a.tw = p->tw(2);
     a.st = p->st[2];
-    {
-        const char* e = getenv("PVD_P5_DEN_STAGED");
-        a.den_ldg = (e && e[0] == '1') ? 0 : 1;
-    }
+    a.vec4 = (p->on[2] % 4 == 0 && a.out_s0 % 4 == 0 && a.out_s1 % 4 == 0 && ((uintptr_t)dose & 15) == 0 &&
+              (!density || (((uintptr_t)density & 15) == 0 && a.den_s0 % 4 == 0 && a.den_s1 % 4 == 0)))
+                 ? 1
+                 : 0;
     const long long nrows = (long long)p->on[0] * p->on[1];
     const long long per = 2LL << p->rowLlog;
-    if (p->fastRows && p->usePipe && p->rowPipeGrid[1] > 0 && nrows < 2000000000LL &&
-        (!density || (((uintptr_t)density & 15) == 0 && a.den_s0 % 4 == 0 && a.den_s1 % 4 == 0))) {
+    if (p->fastRows && p->usePipe && p->rowPipeGrid[1] > 0 && nrows < 2000000000LL) {
         const FastRows* f = p->fastRows;
         const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[1]);
         PVD_LAUNCH(f->invPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);

@@ -154,6 +154,39 @@ int pvd_monoexp_integral(const float* A0, const float* lambda, float t_limit, fl
 int pvd_density_scale(const float* dose, const float* density, float rho_ref, float rho_min, float rho_cut,
                       float scale, float* out, size_t n, void* stream);
 
+/* ======== steps either side of the convolution ======== */
+
+/* ---- TimeCurveFitting.fit_time_activity_curve (time_integration/curve_fitting.py:19-65): per-voxel weighted
+ * least-squares fit of A0 * exp(-lambda t) to T activity volumes (the reference calls scipy.optimize.curve_fit
+ * once per voxel with p0 = [y(t_0), lambda0], sigma = 1/weight_factors), fused with the closed-form integral
+ * accumulated = A0/lambda * (1 - exp(-lambda * t_limit)) (:74-84).  h_vol = HOST array of T device pointers,
+ * h_times / h_weights = HOST arrays of T floats (weights NULL = 1).  A0 / lambda / accumulated are device
+ * outputs of n floats each; any of them may be NULL.  2 <= T <= 16.  Voxels whose fit is not finite get
+ * [0, lambda0] like the reference's except-branch (:58-59). */
+int pvd_monoexp_fit(const float* const* h_vol, const float* h_times, const float* h_weights, int T, float lambda0,
+                    float t_limit, float* A0, float* lambda, float* accumulated, size_t n, void* stream);
+
+/* ---- TissueComposition (tissue/composition.py:48-93) + the A9 density map, one pass over a float32 HU volume:
+ *  - metal_threshold finite: voxels above it are replaced by gaussian_filter(volume with those voxels zeroed,
+ *    sigma = 1, radius 4, 'reflect') evaluated at that voxel (_handle_artifacts :73-93); +INFINITY disables;
+ *  - corrected (nullable): the artifact-handled HU volume;
+ *  - rho (nullable): piecewise-linear HU -> density, h_knots = nk (hu, rho) pairs as pvd_hu_to_density_f32;
+ *  - labels (nullable): one byte per voxel, bit c set when h_ranges[2c] <= HU <= h_ranges[2c+1]
+ *    (calculate_composition :63-67), nr <= 8 ranges. */
+int pvd_ct_prepare(const float* hu, const int n[3], float metal_threshold, const float* h_knots, int nk,
+                   const float* h_ranges, int nr, float* corrected, float* rho, unsigned char* labels, void* stream);
+
+/* ---- calculate_dvh (core/utils.py:233-262), on the device so the dose map need not leave HBM.
+ * mask: device array of n uint8 (mask_is_f32 = 0) or float32 (1); a voxel is in the ROI when mask > 0.
+ * pvd_roi_minmax: min / max / count of the ROI doses -> host (synchronises `stream`); d_scratch16 = 16 bytes of
+ * device memory.  pvd_dvh_histogram: counts per bin with numpy.histogram's uniform-bin rule evaluated in float32
+ * against the device edge array d_edges[bins + 1] (the host builds it with numpy.histogram_bin_edges, as
+ * np.histogram does); d_hist[bins] (uint64, device) is zeroed by the call. */
+int pvd_roi_minmax(const float* dose, const void* mask, int mask_is_f32, size_t n, void* d_scratch16, float* h_min,
+                   float* h_max, unsigned long long* h_count, void* stream);
+int pvd_dvh_histogram(const float* dose, const void* mask, int mask_is_f32, size_t n, const float* d_edges, int bins,
+                      float first_edge, float last_edge, unsigned long long* d_hist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,12 @@ Pinning status
 * A9 density correction, A10 anisotropic spacing, single-timepoint physical-decay dose:
   **parity unpinned** - no reference code exists; the formulas below are the specification.
 
+* Section 8f rows (mono-exponential fit, CT artifact handling / tissue classes, DVH, `.dat` kernels): the
+  restatements call the same SciPy / NumPy routines as the reference and are pinned against the real
+  reference classes by ``oracle/gen_golden.py`` (``tests/golden/next_ref.npz``).  The NIfTI writer of the
+  reference needs nibabel, which is absent here: **NIfTI parity unpinned** (checked against the NIfTI-1
+  field layout and by round trip only).
+
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 """
 from __future__ import annotations
@@ -375,6 +381,105 @@ def conv_same_slabbed(activity: np.ndarray, kernel: np.ndarray, world: int) -> n
         full = conv_reference(pad, k)
         out[lo:hi] = full[K0 - 1 : K0 - 1 + (hi - lo), c1 : c1 + a.shape[1], c2 : c2 + a.shape[2]]
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Section 8f "next" rows: the steps either side of the convolution
+# --------------------------------------------------------------------------------------
+
+
+def fit_monoexp_curvefit(times, activities, half_life: float, weight_factors=None):
+    """Literal restatement of TimeCurveFitting.fit_time_activity_curve
+    (time_integration/curve_fitting.py:36-65): one scipy.optimize.curve_fit call per voxel with
+    p0 = [y(t_0), ln2/half_life], sigma = 1/weight_factors; a raised exception gives [0, decay_constant];
+    accumulated = A0/lambda*(1 - exp(-lambda*100*half_life)) (:74-84).  The arithmetic lives in SciPy
+    (MINPACK lmdif through scipy.optimize.leastsq; the reference pins only scipy>=1.7.0, setup.py)."""
+    import warnings
+
+    from scipy.optimize import curve_fit
+
+    decay_constant = np.log(2) / half_life
+    times = np.array(times)
+    activities = np.array(activities)
+    if weight_factors is None:
+        weight_factors = np.ones_like(times)
+    n_times = len(times)
+    original_shape = activities[0].shape
+    flat = activities.reshape(n_times, -1)
+    fitted = np.zeros((2, flat.shape[1]))
+
+    def decay(t, A0, lam):
+        return A0 * np.exp(-lam * t)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(flat.shape[1]):
+            try:
+                popt, _ = curve_fit(decay, times, flat[:, i], p0=[flat[0, i], decay_constant], sigma=1 / np.array(weight_factors))
+                fitted[:, i] = popt
+            except Exception:
+                fitted[:, i] = [0, decay_constant]
+    integration_limit = 100 * half_life  # curve_fitting.py:78-79
+    acc = fitted[0] / fitted[1] * (1 - np.exp(-fitted[1] * integration_limit))
+    return fitted.reshape((2, *original_shape)), acc.reshape(original_shape)
+
+
+TISSUE_HU_RANGES = {  # tissue/composition.py:40-46
+    "air": (-1000, -900), "lung": (-900, -500), "soft_tissue": (-100, 100), "bone": (300, 3000), "water": (-10, 10),
+}
+
+
+def handle_artifacts(ct_image: np.ndarray) -> np.ndarray:
+    """tissue/composition.py:73-93: metal (> 2000 HU) voxels replaced by gaussian_filter(sigma=1) of the image
+    with those voxels zeroed (NaN -> nan_to_num -> 0)."""
+    from scipy.ndimage import gaussian_filter
+
+    ct_image = np.asarray(ct_image, dtype=np.float64)
+    metal_mask = ct_image > 2000
+    corrected = ct_image.copy()
+    corrected[metal_mask] = np.nan
+    smoothed = gaussian_filter(np.nan_to_num(corrected), sigma=1)
+    corrected[metal_mask] = smoothed[metal_mask]
+    return corrected
+
+
+def tissue_composition(ct_image: np.ndarray, handle: bool = True) -> dict:
+    """tissue/composition.py:48-71: dict of 0/1 float maps per tissue class by inclusive HU range."""
+    ct = handle_artifacts(ct_image) if handle else np.asarray(ct_image, dtype=np.float64)
+    return {name: ((ct >= lo) & (ct <= hi)).astype(float) for name, (lo, hi) in TISSUE_HU_RANGES.items()}
+
+
+def calculate_dvh(dose_map: np.ndarray, roi_mask: np.ndarray, bins: int = 1000):
+    """core/utils.py:233-262, literally: np.histogram over the ROI doses, cumulative volume fraction."""
+    if dose_map.shape != roi_mask.shape:
+        raise ValueError("Dose map and ROI mask must have same dimensions")
+    roi_doses = dose_map[roi_mask > 0]
+    if len(roi_doses) == 0:
+        raise ValueError("ROI mask is empty")
+    hist, edges = np.histogram(roi_doses, bins=bins)
+    cum_dvh = 1.0 - np.cumsum(hist) / len(roi_doses)
+    return edges[1:], cum_dvh
+
+
+def load_kernel_dat(filename):
+    """core/utils.py:17-51, literally (np.fromfile field by field; 80-byte header)."""
+    from datetime import datetime
+
+    with open(filename, "rb") as f:
+        dims = np.fromfile(f, dtype=np.int32, count=3)
+        voxel_size = np.fromfile(f, dtype=np.float32, count=1)[0]
+        total_energy = np.fromfile(f, dtype=np.float32, count=1)[0]
+        scaling = np.fromfile(f, dtype=np.float32, count=1)[0]
+        timestamp = np.fromfile(f, dtype=np.int32, count=6)
+        user = np.fromfile(f, dtype=np.int8, count=32)
+        kernel = np.fromfile(f, dtype=np.float32)
+        kernel = kernel.reshape(dims) * scaling
+    metadata = {
+        "dimensions": dims, "voxel_size": voxel_size, "total_energy": total_energy, "scaling_factor": scaling,
+        "creation_date": datetime(*timestamp).strftime("%Y-%m-%d %H:%M:%S"),
+        "created_by": bytes(user).decode().strip("\x00"),
+    }
+    return kernel, metadata
 
 
 # --------------------------------------------------------------------------------------

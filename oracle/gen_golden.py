@@ -75,6 +75,77 @@ def import_reference():
     return tmp
 
 
+def gen_next_rows(orc):
+    """SURVEY section 8f rows run through the REAL reference: per-voxel curve fit, CT artifact handling + tissue
+    classes, DVH, `.dat` kernel reader.  Own rng so the vectors above never change."""
+    import warnings
+
+    from pyvoxeldosimetry.time_integration.curve_fitting import TimeCurveFitting
+    from pyvoxeldosimetry.tissue.composition import TissueComposition
+    from pyvoxeldosimetry.core import utils as ref_utils
+
+    rng = np.random.default_rng(8061)
+    out = {}
+    # ---- mono-exponential fit (curve_fitting.py:19-65): noisy decaying curves, unweighted and weighted
+    hl = 161.52
+    lam0 = np.log(2) / hl
+    for name, times, shape, noise, weights in (("fit4", [4.0, 24.0, 96.0, 168.0], (5, 4, 6), 0.05, None),
+                                               ("fit3w", [2.0, 20.0, 70.0], (3, 4, 5), 0.10, [1.0, 2.0, 0.5]),
+                                               ("fit6", [1.0, 4.0, 24.0, 48.0, 96.0, 168.0], (2, 3, 4), 0.15, None)):
+        A0 = rng.uniform(1e2, 1e6, shape)
+        lam = lam0 * rng.uniform(0.7, 4.0, shape)
+        maps = [A0 * np.exp(-lam * t) * (1 + noise * rng.standard_normal(shape)) for t in times]
+        maps[-1][0, 0, 0] = maps[-2][0, 0, 0] = 0.0  # a voxel that has decayed to exactly zero
+        for m in maps:
+            m[0, 0, 1] = 0.0                         # an all-zero voxel
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            params, acc = TimeCurveFitting(hl).fit_time_activity_curve(times, maps, weights)
+        p2, a2 = orc.fit_monoexp_curvefit(times, maps, hl, weights)
+        assert np.array_equal(params, p2) and np.array_equal(acc, a2, equal_nan=True), name
+        out[name + "|times"], out[name + "|maps"], out[name + "|params"], out[name + "|acc"] = np.array(times), np.stack(maps), params, acc
+        if weights is not None:
+            out[name + "|weights"] = np.array(weights)
+    # ---- CT: artifact handling + tissue classes (composition.py:48-93)
+    ct = rng.uniform(-1000, 1500, (14, 12, 10))
+    ct[3:6, 4:7, 2:5] = rng.uniform(2100, 3500, (3, 3, 3))  # an implant
+    ct[0, 0, 0] = 2600.0                                      # metal on a corner: exercises 'reflect'
+    ct[13, 11, 9] = 2001.0
+    ct[7, 7, 7], ct[7, 7, 8], ct[8, 8, 8] = -900.0, 100.0, 2000.0  # inclusive range edges / threshold itself
+    tc = TissueComposition()
+    corr = tc._handle_artifacts(ct)
+    comp = tc.calculate_composition(ct, handle_artifacts=True)
+    comp_raw = tc.calculate_composition(ct, handle_artifacts=False)
+    assert np.array_equal(orc.handle_artifacts(ct), corr)
+    for k, v in orc.tissue_composition(ct, True).items():
+        assert np.array_equal(v, comp[k]), k
+    out["ct|hu"], out["ct|corrected"] = ct, corr
+    for k in comp:
+        out[f"ct|comp|{k}"] = comp[k].astype(np.uint8)
+        out[f"ct|comp_raw|{k}"] = comp_raw[k].astype(np.uint8)
+    # ---- DVH (core/utils.py:233-262) on a float32 dose map (the dose path's output type)
+    dose = (rng.gamma(2.0, 5.0, (9, 8, 7)) * 1e3).astype(np.float32)
+    mask = rng.uniform(0, 1, dose.shape) > 0.4
+    for bins in (1000, 17):
+        e, c = ref_utils.calculate_dvh(dose, mask, bins)
+        e2, c2 = orc.calculate_dvh(dose, mask, bins)
+        assert np.array_equal(e, e2) and np.array_equal(c, c2)
+        out[f"dvh|edges{bins}"], out[f"dvh|cum{bins}"] = e, c
+    out["dvh|dose"], out["dvh|mask"] = dose, mask.astype(np.uint8)
+    # ---- `.dat` kernel file: bytes laid out per utils.py:31-41, parsed by the reference reader
+    k = rng.uniform(0, 1, (4, 5, 6)).astype(np.float32)
+    import struct
+    blob = struct.pack("<3i3f6i", 4, 5, 6, 1.5, 0.9337, 2.0, 2025, 2, 8, 9, 50, 56) + b"devhliu".ljust(32, b"\x00") + k.tobytes()
+    path = os.path.join(tempfile.mkdtemp(prefix="pvd_dat_"), "k.dat")
+    with open(path, "wb") as f:
+        f.write(blob)
+    kr, md = ref_utils.load_kernel(path)
+    ko, mo = orc.load_kernel_dat(path)
+    assert np.array_equal(kr, ko) and md["creation_date"] == mo["creation_date"] == "2025-02-08 09:50:56" and md["created_by"] == "devhliu"
+    out["dat|blob"], out["dat|kernel"] = np.frombuffer(blob, dtype=np.uint8), kr
+    np.savez_compressed(os.path.join(OUT, "next_ref.npz"), **out)
+
+
 def main():
     tmp = import_reference()
     sys.path.insert(0, REPO)
@@ -194,6 +265,7 @@ def main():
     })
     # keep three orthogonal central planes through the peak (8,8,8) as array fixtures (small)
     np.savez_compressed(os.path.join(OUT, "c1_ref.npz"), plane_x8=d1[8], plane_y8=d1[:, 8], plane_z8=d1[:, :, 8])
+    gen_next_rows(orc)
     with open(os.path.join(OUT, "kats.json"), "w") as f:
         json.dump({k: float(v) for k, v in kats.items()}, f, indent=1, sort_keys=True)
     shutil.rmtree(tmp, ignore_errors=True)

@@ -24,7 +24,7 @@ SYMBOLS = [
     "pvd_version", "pvd_last_error", "pvd_good_fft_size", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
     "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times",
     "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
-    "pvd_density_scale",
+    "pvd_density_scale", "pvd_monoexp_fit", "pvd_ct_prepare", "pvd_roi_minmax", "pvd_dvh_histogram",
 ]
 
 
@@ -90,6 +90,10 @@ class PvdLib:
         d.pvd_weighted_sum.argtypes = [C.POINTER(vp), fp, C.c_int, vp, C.c_size_t, vp]
         d.pvd_monoexp_integral.argtypes = [vp, vp, C.c_float, vp, C.c_size_t, vp]
         d.pvd_density_scale.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, C.c_size_t, vp]
+        d.pvd_monoexp_fit.argtypes = [C.POINTER(vp), fp, fp, C.c_int, C.c_float, C.c_float, vp, vp, vp, C.c_size_t, vp]
+        d.pvd_ct_prepare.argtypes = [vp, ip, C.c_float, fp, C.c_int, fp, C.c_int, vp, vp, vp, vp]
+        d.pvd_roi_minmax.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, fp, fp, C.POINTER(C.c_ulonglong), vp]
+        d.pvd_dvh_histogram.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, C.c_int, C.c_float, C.c_float, vp, vp]
 
     # ------------------------------------------------------------------ helpers
     def check(self, rc: int):
@@ -181,6 +185,34 @@ class PvdLib:
     def density_scale(self, dose_ptr: int, den_ptr: int, rho_ref: float, rho_min: float, rho_cut: float, scale: float,
                       out_ptr: int, n: int, stream: int = 0):
         self.check(self.dll.pvd_density_scale(dose_ptr, den_ptr, rho_ref, rho_min, rho_cut, scale, out_ptr, n, stream))
+
+
+    def monoexp_fit(self, vol_ptrs: Sequence[int], times: Sequence[float], weights: Optional[Sequence[float]], lambda0: float,
+                    t_limit: float, a0_ptr: Optional[int], lam_ptr: Optional[int], acc_ptr: Optional[int], n: int, stream: int = 0):
+        T = len(vol_ptrs)
+        ptrs = (C.c_void_p * T)(*vol_ptrs)
+        t = (C.c_float * T)(*[float(x) for x in times])
+        w = (C.c_float * T)(*[float(x) for x in weights]) if weights is not None else None
+        self.check(self.dll.pvd_monoexp_fit(ptrs, t, w, T, lambda0, t_limit, a0_ptr, lam_ptr, acc_ptr, n, stream))
+
+    def ct_prepare(self, hu_ptr: int, shape, metal_threshold: float, knots, ranges, corrected_ptr: Optional[int],
+                   rho_ptr: Optional[int], labels_ptr: Optional[int], stream: int = 0):
+        kflat = [float(v) for pair in (knots or []) for v in pair]
+        rflat = [float(v) for pair in (ranges or []) for v in pair]
+        karr = (C.c_float * len(kflat))(*kflat) if kflat else None
+        rarr = (C.c_float * len(rflat))(*rflat) if rflat else None
+        self.check(self.dll.pvd_ct_prepare(hu_ptr, _i3(shape), float(metal_threshold), karr, len(kflat) // 2, rarr, len(rflat) // 2,
+                                           corrected_ptr, rho_ptr, labels_ptr, stream))
+
+    def roi_minmax(self, dose_ptr: int, mask_ptr: int, mask_is_f32: bool, n: int, scratch_ptr: int, stream: int = 0):
+        mn, mx, cnt = C.c_float(), C.c_float(), C.c_ulonglong()
+        self.check(self.dll.pvd_roi_minmax(dose_ptr, mask_ptr, 1 if mask_is_f32 else 0, n, scratch_ptr, C.byref(mn), C.byref(mx),
+                                           C.byref(cnt), stream))
+        return mn.value, mx.value, cnt.value
+
+    def dvh_histogram(self, dose_ptr: int, mask_ptr: int, mask_is_f32: bool, n: int, edges_ptr: int, bins: int, first: float,
+                      last: float, hist_ptr: int, stream: int = 0):
+        self.check(self.dll.pvd_dvh_histogram(dose_ptr, mask_ptr, 1 if mask_is_f32 else 0, n, edges_ptr, bins, first, last, hist_ptr, stream))
 
 
 _LIB: Optional[PvdLib] = None

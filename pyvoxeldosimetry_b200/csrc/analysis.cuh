@@ -1,0 +1,323 @@
+// Kernels for the steps either side of the convolution:
+//   * per-voxel mono-exponential time-activity fit + closed-form integral (feeds the convolution),
+//   * CT preparation: metal-artifact fill, HU -> density and tissue-class labels (feeds the density correction),
+//   * dose-volume histogram of a dose map over an ROI mask (consumes the dose map on the device).
+// All are single-pass, bandwidth-bound elementwise / reduction kernels.
+#pragma once
+#include "elementwise.cuh"
+
+#ifdef PVD_EMULATE
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+static inline unsigned atomicMin(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
+static inline unsigned __float_as_uint(float f) {
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+using std::isfinite;
+#endif
+
+namespace pvd {
+
+// ------------------------------------------------------------------------------------------------
+// Mono-exponential fit  y(t) = A0 exp(-lambda t), weighted least squares  sum_i (w_i (y_i - f(t_i)))^2
+// (reference: time_integration/curve_fitting.py:46-59 - one scipy.optimize.curve_fit call per voxel with
+// p0 = [y(t_0), ln2/half_life], sigma = 1/weight_factors).  Per voxel, in registers:
+//   1. 16 damped Gauss-Newton (Levenberg-Marquardt) steps on (A0, lambda) from the reference's p0 - the
+//      globalisation: a step is accepted only if the cost does not increase;
+//   2. 4 Newton steps on the variable-projection stationarity condition h(lambda) = P Q1 - Q P1 = 0
+//      (P = sum w^2 y e, Q = sum w^2 e^2, P1 = sum w^2 y t e, Q1 = sum w^2 t e^2, e = exp(-lambda t)), which
+//      polishes lambda to float32 round-off; A0 = P/Q is the exact linear optimum for that lambda.
+// A voxel whose result is not finite or whose Jacobian is rank-deficient at the end point (no finite minimiser)
+// gets [0, lambda0], as the reference does when curve_fit raises (:58-59).
+// The integral A0/lambda (1 - exp(-lambda T_lim)) (curve_fitting.py:74-84) is fused into the same pass.
+struct FitArgs {
+    const float* v[kMaxT];
+    float t[kMaxT];
+    float w[kMaxT];
+    int T;
+    float lam0, tlim;
+};
+
+template <int TT>  // TT = compile-time number of time points (0: runtime, up to kMaxT)
+__global__ void monoexp_fit_kernel(const FitArgs a, float* __restrict__ A0out, float* __restrict__ lamout,
+                                   float* __restrict__ accout, size_t n) {
+    constexpr int TM = TT > 0 ? TT : kMaxT;
+    const int T = TT > 0 ? TT : a.T;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float y[TM];
+        PVD_UNROLL
+        for (int k = 0; k < TM; ++k) y[k] = (k < T) ? __ldg(a.v[k] + i) : 0.f;
+        auto cost = [&](float A, float lam) {
+            float c = 0.f;
+            PVD_UNROLL
+            for (int k = 0; k < TM; ++k)
+                if (k < T) {
+                    const float r = a.w[k] * (y[k] - A * expf(-lam * a.t[k]));
+                    c += r * r;
+                }
+            return c;
+        };
+        float A = y[0], lam = a.lam0, mu = 1e-3f;
+        float c = cost(A, lam);
+        for (int it = 0; it < 16; ++it) {
+            float a11 = 0.f, a12 = 0.f, a22 = 0.f, g1 = 0.f, g2 = 0.f;
+            PVD_UNROLL
+            for (int k = 0; k < TM; ++k)
+                if (k < T) {
+                    const float e = expf(-lam * a.t[k]);
+                    const float ja = a.w[k] * e, jl = -a.w[k] * A * a.t[k] * e;
+                    const float r = a.w[k] * (y[k] - A * e);
+                    a11 += ja * ja;
+                    a12 += ja * jl;
+                    a22 += jl * jl;
+                    g1 += ja * r;
+                    g2 += jl * r;
+                }
+            const float d11 = a11 * (1.f + mu), d22 = a22 * (1.f + mu) + (a22 == 0.f ? 1.f : 0.f);
+            float det = d11 * d22 - a12 * a12;
+            if (det == 0.f) det = 1.f;
+            const float An = A + (d22 * g1 - a12 * g2) / det, ln = lam + (d11 * g2 - a12 * g1) / det;
+            const float cn = cost(An, ln);
+            const bool ok = cn <= c;  // false for NaN
+            if (ok) {
+                A = An;
+                lam = ln;
+                c = cn;
+            }
+            mu = fminf(fmaxf(ok ? mu * 0.2f : mu * 10.f, 1e-9f), 1e9f);
+        }
+        float P = 0.f, Q = 0.f, h = 0.f, dh = 0.f;
+        auto hfun = [&](float l, float& P_, float& Q_, float& h_, float& dh_) {
+            float p = 0.f, q = 0.f, p1 = 0.f, q1 = 0.f, p2 = 0.f, q2 = 0.f;
+            PVD_UNROLL
+            for (int k = 0; k < TM; ++k)
+                if (k < T) {
+                    const float e = expf(-l * a.t[k]), w2 = a.w[k] * a.w[k], t = a.t[k];
+                    const float wye = w2 * y[k] * e, wee = w2 * e * e;
+                    p += wye;
+                    q += wee;
+                    p1 += wye * t;
+                    q1 += wee * t;
+                    p2 += wye * t * t;
+                    q2 += wee * t * t;
+                }
+            P_ = p;
+            Q_ = q;
+            h_ = p * q1 - q * p1;
+            dh_ = -p1 * q1 - 2.f * p * q2 + 2.f * q1 * p1 + q * p2;
+        };
+        hfun(lam, P, Q, h, dh);
+        for (int it = 0; it < 4; ++it) {
+            const float ln = lam - (dh != 0.f ? h / dh : 0.f);
+            float Pn, Qn, hn, dhn;
+            hfun(ln, Pn, Qn, hn, dhn);
+            if (fabsf(hn) < fabsf(h)) {
+                lam = ln;
+                P = Pn;
+                Q = Qn;
+                h = hn;
+                dh = dhn;
+            }
+        }
+        A = Q > 0.f ? P / Q : 0.f;
+        // Ill-posed curves (e.g. activity that drops to zero after the first point) have no finite minimiser:
+        // lambda runs away, curve_fit raises and the reference stores [0, lambda0].  Here that shows as a
+        // rank-deficient Jacobian at the end point: det(J^T J) <= 1e-5 a11 a22 (well-posed fits sit at 0.3-0.7).
+        {
+            float a11 = 0.f, a12 = 0.f, a22 = 0.f;
+            PVD_UNROLL
+            for (int k = 0; k < TM; ++k)
+                if (k < T) {
+                    const float e = expf(-lam * a.t[k]);
+                    const float ja = a.w[k] * e, jl = a.w[k] * a.t[k] * e;  // d/dlambda without the common factor -A
+                    a11 += ja * ja;
+                    a12 += ja * jl;
+                    a22 += jl * jl;
+                }
+            const bool rank_ok = (a11 * a22 - a12 * a12) > 1e-5f * (a11 * a22);
+            if (!(isfinite(A) && isfinite(lam)) || (A != 0.f && !rank_ok)) {
+                A = 0.f;
+                lam = a.lam0;
+            }
+        }
+        if (A0out) A0out[i] = A;
+        if (lamout) lamout[i] = lam;
+        if (accout) accout[i] = A / lam * (-expm1f(-lam * a.tlim));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CT preparation.  One pass over the CT volume (float32 HU):
+//   * metal-artifact fill (reference tissue/composition.py:73-93): voxels above the threshold are replaced
+//     by the value at that voxel of gaussian_filter(ct with those voxels zeroed, sigma=1) - scipy defaults:
+//     radius 4 (truncate 4.0), 'reflect' boundary.  Only metal voxels need the 9^3 gather, so it is
+//     evaluated at those voxels only (weights g(dx) g(dy) g(dz), identical to the separable passes);
+//   * HU -> mass density by the piecewise-linear knot table (A9 helper);
+//   * tissue-class bit mask, bit c set when lo_c <= HU <= hi_c (composition.py:63-67, ranges :40-46).
+struct CtArgs {
+    const float* hu;
+    int n0, n1, n2;
+    float metal_thr;  // +inf disables the fill
+    float g[5];       // normalised Gaussian weights for |d| = 0..4
+    Knots knots;      // nk == 0: no density output
+    int nr;
+    float lo[8], hi[8];
+    float* corrected;
+    float* rho;
+    unsigned char* labels;
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // scipy 'reflect': (d c b a | a b c d | d c b a)
+    while (i < 0 || i >= n) i = (i < 0) ? (-i - 1) : (2 * n - 1 - i);
+    return i;
+}
+
+__global__ void ct_prepare_kernel(const CtArgs a) {
+    const size_t n = (size_t)a.n0 * a.n1 * a.n2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float h = a.hu[i];
+        if (h > a.metal_thr) {
+            const int z = (int)(i % a.n2);
+            const size_t r = i / a.n2;
+            const int y = (int)(r % a.n1), x = (int)(r / a.n1);
+            float acc = 0.f;
+            for (int dx = -4; dx <= 4; ++dx) {
+                const size_t ox = (size_t)reflect_idx(x + dx, a.n0) * a.n1;
+                const float gx = a.g[dx < 0 ? -dx : dx];
+                for (int dy = -4; dy <= 4; ++dy) {
+                    const size_t oy = (ox + reflect_idx(y + dy, a.n1)) * a.n2;
+                    const float gxy = gx * a.g[dy < 0 ? -dy : dy];
+                    float line = 0.f;
+                    for (int dz = -4; dz <= 4; ++dz) {
+                        const float v = __ldg(a.hu + oy + reflect_idx(z + dz, a.n2));
+                        line += a.g[dz < 0 ? -dz : dz] * (v > a.metal_thr ? 0.f : v);
+                    }
+                    acc += gxy * line;
+                }
+            }
+            h = acc;
+        }
+        if (a.corrected) a.corrected[i] = h;
+        if (a.rho) {
+            const Knots& k = a.knots;
+            float rr;
+            if (h <= k.hu[0]) {
+                rr = k.rho[0];
+            } else if (h >= k.hu[k.nk - 1]) {
+                rr = k.rho[k.nk - 1];
+            } else {
+                int j = 1;
+                while (h > k.hu[j]) ++j;
+                const float t = (h - k.hu[j - 1]) / (k.hu[j] - k.hu[j - 1]);
+                rr = k.rho[j - 1] + t * (k.rho[j] - k.rho[j - 1]);
+            }
+            a.rho[i] = rr;
+        }
+        if (a.labels) {
+            unsigned m = 0;
+            for (int c = 0; c < a.nr; ++c) m |= (h >= a.lo[c] && h <= a.hi[c]) ? (1u << c) : 0u;
+            a.labels[i] = (unsigned char)m;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dose-volume histogram (reference core/utils.py:233-262: np.histogram(dose[mask > 0], bins) + cumulative).
+// Pass 1: min / max / count of the ROI doses.  Floats are mapped to order-preserving unsigned keys so one
+// atomicMin/atomicMax per block suffices.  Pass 2: bin counts with numpy's uniform-bin rule, reproduced
+// operation by operation in float32 (numpy/lib/_histograms_impl.py: index = int((x - first) / (last - first) * bins),
+// clamp of the last edge, then the two corrections against the edge array, which the host computes with
+// np.linspace exactly as numpy does) - so the counts are bit-identical to numpy's on the same float32 doses.
+__device__ __forceinline__ unsigned f2key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct RoiStats {
+    unsigned min_key, max_key;
+    unsigned long long count;
+};
+
+template <class M>
+__global__ void roi_minmax_kernel(const float* __restrict__ dose, const M* __restrict__ mask, size_t n, RoiStats* out) {
+    __shared__ unsigned s_min, s_max;
+    __shared__ unsigned long long s_cnt;
+    if (threadIdx.x == 0) {
+        s_min = 0xFFFFFFFFu;
+        s_max = 0u;
+        s_cnt = 0ull;
+    }
+    __syncthreads();
+    unsigned lo = 0xFFFFFFFFu, hi = 0u;
+    unsigned long long cnt = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (mask[i] > (M)0) {
+            const unsigned k = f2key(dose[i]);
+            lo = k < lo ? k : lo;
+            hi = k > hi ? k : hi;
+            ++cnt;
+        }
+    }
+    if (cnt) {
+        atomicMin(&s_min, lo);
+        atomicMax(&s_max, hi);
+        atomicAdd(&s_cnt, cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) {
+        atomicMin(&out->min_key, s_min);
+        atomicMax(&out->max_key, s_max);
+        atomicAdd(&out->count, s_cnt);
+    }
+}
+
+constexpr int kDvhSmemBins = 4096;
+
+template <class M>
+__global__ void dvh_hist_kernel(const float* __restrict__ dose, const M* __restrict__ mask, size_t n,
+                                const float* __restrict__ edges, int bins, float first, float last,
+                                unsigned long long* __restrict__ hist) {
+    __shared__ unsigned s_hist[kDvhSmemBins];
+    const bool use_smem = bins <= kDvhSmemBins;
+    if (use_smem) {
+        for (int b = threadIdx.x; b < bins; b += blockDim.x) s_hist[b] = 0u;
+        __syncthreads();
+    }
+    const float denom = __fsub_rn(last, first);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!(mask[i] > (M)0)) continue;
+        const float x = dose[i];
+        if (!(x >= first && x <= last)) continue;  // NaN doses are dropped, as numpy's `keep` mask does
+        int idx = (int)__fmul_rn(__fdiv_rn(__fsub_rn(x, first), denom), (float)bins);
+        if (idx == bins) --idx;
+        if (x < edges[idx]) --idx;
+        else if (idx != bins - 1 && x >= edges[idx + 1]) ++idx;
+        if (use_smem) atomicAdd(&s_hist[idx], 1u);
+        else atomicAdd(&hist[idx], 1ull);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < bins; b += blockDim.x)
+            if (s_hist[b]) atomicAdd(&hist[b], (unsigned long long)s_hist[b]);
+    }
+}
+
+}  // namespace pvd

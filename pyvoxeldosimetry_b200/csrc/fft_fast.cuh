@@ -284,7 +284,26 @@ __global__ void __launch_bounds__(NT) rows_fwd_fast_kernel(const RowFwdArgs g) {
             float acc[ZIT];
             PVD_UNROLL
             for (int i = 0; i < ZIT; ++i) acc[i] = 0.f;
-            for (int t = 0; t < T; ++t) {
+            int t = 0;
+            for (; t + 4 <= T; t += 4) {  // four time points per batch: 4 * ZIT independent loads in flight per lane
+                float v[4][ZIT];
+                PVD_UNROLL
+                for (int q = 0; q < 4; ++q) {
+                    const float* __restrict__ pt = g.in[t + q] + off;
+                    PVD_UNROLL
+                    for (int i = 0; i < ZIT; ++i) {
+                        const int z = lane + 32 * i;
+                        v[q][i] = (valid && z < n2) ? __ldg(pt + z) : 0.f;
+                    }
+                }
+                PVD_UNROLL
+                for (int q = 0; q < 4; ++q) {
+                    const float wt = g.w[t + q];
+                    PVD_UNROLL
+                    for (int i = 0; i < ZIT; ++i) acc[i] = fmaf(wt, v[q][i], acc[i]);
+                }
+            }
+            for (; t < T; ++t) {
                 const float* __restrict__ pt = g.in[t] + off;
                 const float wt = g.w[t];
                 PVD_UNROLL

@@ -8,7 +8,7 @@
 #include <vector>
 
 #include "direct_conv.cuh"
-#include "elementwise.cuh"
+#include "analysis.cuh"
 #include "fft_fast.cuh"
 #include "fft_pipe.cuh"
 #include "fft_pipe2.cuh"
@@ -897,6 +897,129 @@ int pvd_density_scale(const float* dose, const float* density, float rho_ref, fl
     PVD_LAUNCH(density_scale_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, dose, density, rho_ref, rho_min,
                rho_cut, scale, out, n);
     PVD_CUDA_CHECK("density_scale_kernel");
+    return PVD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// steps either side of the convolution (analysis.cuh)
+int pvd_monoexp_fit(const float* const* h_vol, const float* h_times, const float* h_weights, int T, float lambda0,
+                    float t_limit, float* A0, float* lambda, float* accumulated, size_t n, void* stream) {
+    if (!h_vol || !h_times) return fail(PVD_ERR_INVALID, "null argument");
+    if (T < 2 || T > PVD_MAX_T) return fail(PVD_ERR_INVALID, "T=%d outside [2,%d]: a two-parameter fit needs two time points", T, PVD_MAX_T);
+    if (!(lambda0 > 0.f)) return fail(PVD_ERR_INVALID, "lambda0 must be positive");
+    FitArgs a;
+    memset(&a, 0, sizeof a);
+    a.T = T;
+    a.lam0 = lambda0;
+    a.tlim = t_limit;
+    for (int t = 0; t < T; ++t) {
+        if (!h_vol[t]) return fail(PVD_ERR_INVALID, "volume pointer %d is null", t);
+        a.v[t] = h_vol[t];
+        a.t[t] = h_times[t];
+        a.w[t] = h_weights ? h_weights[t] : 1.f;
+    }
+    if (n == 0) return PVD_OK;
+    const dim3 grid(ew_grid(n)), block(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (T) {
+        case 2: PVD_LAUNCH(monoexp_fit_kernel<2>, grid, block, 0, st, a, A0, lambda, accumulated, n); break;
+        case 3: PVD_LAUNCH(monoexp_fit_kernel<3>, grid, block, 0, st, a, A0, lambda, accumulated, n); break;
+        case 4: PVD_LAUNCH(monoexp_fit_kernel<4>, grid, block, 0, st, a, A0, lambda, accumulated, n); break;
+        case 5: PVD_LAUNCH(monoexp_fit_kernel<5>, grid, block, 0, st, a, A0, lambda, accumulated, n); break;
+        case 6: PVD_LAUNCH(monoexp_fit_kernel<6>, grid, block, 0, st, a, A0, lambda, accumulated, n); break;
+        default: PVD_LAUNCH(monoexp_fit_kernel<0>, grid, block, 0, st, a, A0, lambda, accumulated, n); break;
+    }
+    PVD_CUDA_CHECK("monoexp_fit_kernel");
+    return PVD_OK;
+}
+
+int pvd_ct_prepare(const float* hu, const int n[3], float metal_threshold, const float* h_knots, int nk,
+                   const float* h_ranges, int nr, float* corrected, float* rho, unsigned char* labels, void* stream) {
+    if (!hu || !n) return fail(PVD_ERR_INVALID, "null argument");
+    if (n[0] < 1 || n[1] < 1 || n[2] < 1) return fail(PVD_ERR_INVALID, "extents must be positive");
+    if (hu == corrected) return fail(PVD_ERR_INVALID, "the artifact fill reads neighbours: corrected must not alias hu");
+    CtArgs a;
+    memset(&a, 0, sizeof a);
+    a.hu = hu;
+    a.n0 = n[0];
+    a.n1 = n[1];
+    a.n2 = n[2];
+    a.metal_thr = metal_threshold;
+    {  // scipy.ndimage._filters._gaussian_kernel1d(sigma = 1, order = 0, radius = 4): exp(-x^2/2) normalised to sum 1
+        double gsum = 0.0, gw[5];
+        for (int d = 0; d <= 4; ++d) {
+            gw[d] = std::exp(-0.5 * d * d);
+            gsum += (d ? 2.0 : 1.0) * gw[d];
+        }
+        for (int d = 0; d <= 4; ++d) a.g[d] = (float)(gw[d] / gsum);
+    }
+    if (rho) {
+        if (int rc = fill_knots(h_knots, nk, a.knots)) return rc;
+    }
+    if (labels) {
+        if (!h_ranges || nr < 1 || nr > 8) return fail(PVD_ERR_INVALID, "labels need 1..8 (lo, hi) HU ranges");
+        a.nr = nr;
+        for (int c = 0; c < nr; ++c) {
+            a.lo[c] = h_ranges[2 * c];
+            a.hi[c] = h_ranges[2 * c + 1];
+        }
+    }
+    a.corrected = corrected;
+    a.rho = rho;
+    a.labels = labels;
+    const size_t nv = (size_t)n[0] * n[1] * n[2];
+    PVD_LAUNCH(ct_prepare_kernel, dim3(ew_grid(nv)), dim3(256), 0, (cudaStream_t)stream, a);
+    PVD_CUDA_CHECK("ct_prepare_kernel");
+    return PVD_OK;
+}
+
+int pvd_roi_minmax(const float* dose, const void* mask, int mask_is_f32, size_t n, void* d_scratch16, float* h_min,
+                   float* h_max, unsigned long long* h_count, void* stream) {
+    if (!dose || !mask || !d_scratch16 || !h_min || !h_max || !h_count) return fail(PVD_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    RoiStats init;
+    init.min_key = 0xFFFFFFFFu;
+    init.max_key = 0u;
+    init.count = 0ull;
+    RoiStats* d = reinterpret_cast<RoiStats*>(d_scratch16);
+    if (cudaMemcpyAsync(d, &init, sizeof init, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(PVD_ERR_CUDA, "cudaMemcpyAsync failed");
+    if (n) {
+        if (mask_is_f32)
+            PVD_LAUNCH(roi_minmax_kernel<float>, dim3(ew_grid(n)), dim3(256), 0, st, dose, (const float*)mask, n, d);
+        else
+            PVD_LAUNCH(roi_minmax_kernel<unsigned char>, dim3(ew_grid(n)), dim3(256), 0, st, dose, (const unsigned char*)mask, n, d);
+        PVD_CUDA_CHECK("roi_minmax_kernel");
+    }
+    RoiStats h;
+    if (cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+        return fail(PVD_ERR_CUDA, "reading the ROI statistics failed");
+    auto key2f = [](unsigned k) {
+        const unsigned u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    *h_count = h.count;
+    *h_min = h.count ? key2f(h.min_key) : 0.f;
+    *h_max = h.count ? key2f(h.max_key) : 0.f;
+    return PVD_OK;
+}
+
+int pvd_dvh_histogram(const float* dose, const void* mask, int mask_is_f32, size_t n, const float* d_edges, int bins,
+                      float first_edge, float last_edge, unsigned long long* d_hist, void* stream) {
+    if (!dose || !mask || !d_edges || !d_hist) return fail(PVD_ERR_INVALID, "null argument");
+    if (bins < 1) return fail(PVD_ERR_INVALID, "bins must be positive");
+    if (!(last_edge > first_edge)) return fail(PVD_ERR_INVALID, "last_edge must exceed first_edge");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(d_hist, 0, (size_t)bins * sizeof(unsigned long long), st) != cudaSuccess) return fail(PVD_ERR_CUDA, "cudaMemsetAsync failed");
+    if (n == 0) return PVD_OK;
+    if (mask_is_f32)
+        PVD_LAUNCH(dvh_hist_kernel<float>, dim3(ew_grid(n)), dim3(256), 0, st, dose, (const float*)mask, n, d_edges, bins,
+                   first_edge, last_edge, d_hist);
+    else
+        PVD_LAUNCH(dvh_hist_kernel<unsigned char>, dim3(ew_grid(n)), dim3(256), 0, st, dose, (const unsigned char*)mask, n,
+                   d_edges, bins, first_edge, last_edge, d_hist);
+    PVD_CUDA_CHECK("dvh_hist_kernel");
     return PVD_OK;
 }
 

@@ -233,3 +233,58 @@ def density_scale(dose: torch.Tensor, density: torch.Tensor, rho_ref=1.0, rho_mi
         get_lib().density_scale(dose.data_ptr(), density.data_ptr(), rho_ref, rho_min, rho_cut, scale, out.data_ptr(),
                                 dose.numel(), _stream_ptr(dev))
     return out
+
+
+# ---------------------------------------------------------------------------- steps either side of the convolution
+def monoexp_fit(vols: Sequence[torch.Tensor], times: Sequence[float], weights: Optional[Sequence[float]], lambda0: float,
+                t_limit: float, want_params: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+    """Per-voxel weighted mono-exponential fit + integral on the device.
+    -> (params [2, *shape] or None, accumulated [*shape]); inputs are float32 CUDA tensors of one shape."""
+    dev = require_cuda(vols[0].device)
+    T = len(vols)
+    if T > MAX_T:
+        raise ValueError(f"at most {MAX_T} time points")
+    shape = tuple(vols[0].shape)
+    params = torch.empty((2,) + shape, dtype=torch.float32, device=dev) if want_params else None
+    acc = torch.empty(shape, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        get_lib().monoexp_fit([v.data_ptr() for v in vols], times, weights, float(lambda0), float(t_limit),
+                              params[0].data_ptr() if want_params else None, params[1].data_ptr() if want_params else None,
+                              acc.data_ptr(), acc.numel(), _stream_ptr(dev))
+    return params, acc
+
+
+def ct_prepare(hu: torch.Tensor, metal_threshold: float, knots=None, ranges=None, want_corrected: bool = True):
+    """One pass over a float32 HU volume -> (corrected HU | None, density | None, tissue bit labels | None)."""
+    dev = require_cuda(hu.device)
+    if hu.dim() != 3:
+        raise ValueError("CT volume must be 3-D")
+    hu = hu.to(torch.float32).contiguous()
+    corrected = torch.empty_like(hu) if want_corrected else None
+    rho = torch.empty_like(hu) if knots else None
+    labels = torch.empty(hu.shape, dtype=torch.uint8, device=dev) if ranges else None
+    with torch.cuda.device(dev):
+        get_lib().ct_prepare(hu.data_ptr(), tuple(hu.shape), metal_threshold, knots, ranges,
+                             None if corrected is None else corrected.data_ptr(), None if rho is None else rho.data_ptr(),
+                             None if labels is None else labels.data_ptr(), _stream_ptr(dev))
+    return corrected, rho, labels
+
+
+def roi_minmax(dose: torch.Tensor, mask: torch.Tensor) -> Tuple[float, float, int]:
+    dev = require_cuda(dose.device)
+    scratch = torch.empty(16, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        return get_lib().roi_minmax(dose.data_ptr(), mask.data_ptr(), mask.dtype == torch.float32, dose.numel(),
+                                    scratch.data_ptr(), _stream_ptr(dev))
+
+
+def dvh_histogram(dose: torch.Tensor, mask: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
+    """Counts per bin (int64 CUDA tensor) of dose[mask > 0] for the uniform float32 edge array `edges` (CUDA)."""
+    dev = require_cuda(dose.device)
+    bins = edges.numel() - 1
+    hist = torch.empty(bins, dtype=torch.int64, device=dev)
+    e = edges.cpu()
+    with torch.cuda.device(dev):
+        get_lib().dvh_histogram(dose.data_ptr(), mask.data_ptr(), mask.dtype == torch.float32, dose.numel(), edges.data_ptr(),
+                                bins, float(e[0]), float(e[-1]), hist.data_ptr(), _stream_ptr(dev))
+    return hist

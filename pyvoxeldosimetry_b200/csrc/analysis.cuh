@@ -8,6 +8,7 @@
 
 #ifdef PVD_EMULATE
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
@@ -40,9 +41,9 @@ namespace pvd {
 // Mono-exponential fit  y(t) = A0 exp(-lambda t), weighted least squares  sum_i (w_i (y_i - f(t_i)))^2
 // (reference: time_integration/curve_fitting.py:46-59 - one scipy.optimize.curve_fit call per voxel with
 // p0 = [y(t_0), ln2/half_life], sigma = 1/weight_factors).  Per voxel, in registers:
-//   1. 16 damped Gauss-Newton (Levenberg-Marquardt) steps on (A0, lambda) from the reference's p0 - the
-//      globalisation: a step is accepted only if the cost does not increase;
-//   2. 4 Newton steps on the variable-projection stationarity condition h(lambda) = P Q1 - Q P1 = 0
+//   1. up to 16 damped Gauss-Newton (Levenberg-Marquardt) steps on (A0, lambda) from the reference's p0 - the
+//      globalisation: a step is accepted only if the cost does not increase; stops when the cost stalls;
+//   2. up to 4 Newton steps on the variable-projection stationarity condition h(lambda) = P Q1 - Q P1 = 0
 //      (P = sum w^2 y e, Q = sum w^2 e^2, P1 = sum w^2 y t e, Q1 = sum w^2 t e^2, e = exp(-lambda t)), which
 //      polishes lambda to float32 round-off; A0 = P/Q is the exact linear optimum for that lambda.
 // A voxel whose result is not finite or whose Jacobian is rank-deficient at the end point (no finite minimiser)
@@ -65,26 +66,23 @@ __global__ void monoexp_fit_kernel(const FitArgs a, float* __restrict__ A0out, f
         float y[TM];
         PVD_UNROLL
         for (int k = 0; k < TM; ++k) y[k] = (k < T) ? __ldg(a.v[k] + i) : 0.f;
-        auto cost = [&](float A, float lam) {
-            float c = 0.f;
-            PVD_UNROLL
-            for (int k = 0; k < TM; ++k)
-                if (k < T) {
-                    const float r = a.w[k] * (y[k] - A * expf(-lam * a.t[k]));
-                    c += r * r;
-                }
-            return c;
-        };
-        float A = y[0], lam = a.lam0, mu = 1e-3f;
-        float c = cost(A, lam);
+        // e[k] = exp(-lambda t_k) at the current iterate is carried along: one set of exponentials per step
+        float e[TM];
+        float A = y[0], lam = a.lam0, mu = 1e-3f, c = 0.f;
+        PVD_UNROLL
+        for (int k = 0; k < TM; ++k)
+            if (k < T) {
+                e[k] = expf(-lam * a.t[k]);
+                const float r = a.w[k] * (y[k] - A * e[k]);
+                c += r * r;
+            }
         for (int it = 0; it < 16; ++it) {
             float a11 = 0.f, a12 = 0.f, a22 = 0.f, g1 = 0.f, g2 = 0.f;
             PVD_UNROLL
             for (int k = 0; k < TM; ++k)
                 if (k < T) {
-                    const float e = expf(-lam * a.t[k]);
-                    const float ja = a.w[k] * e, jl = -a.w[k] * A * a.t[k] * e;
-                    const float r = a.w[k] * (y[k] - A * e);
+                    const float ja = a.w[k] * e[k], jl = -a.w[k] * A * a.t[k] * e[k];
+                    const float r = a.w[k] * (y[k] - A * e[k]);
                     a11 += ja * ja;
                     a12 += ja * jl;
                     a22 += jl * jl;
@@ -95,14 +93,28 @@ __global__ void monoexp_fit_kernel(const FitArgs a, float* __restrict__ A0out, f
             float det = d11 * d22 - a12 * a12;
             if (det == 0.f) det = 1.f;
             const float An = A + (d22 * g1 - a12 * g2) / det, ln = lam + (d11 * g2 - a12 * g1) / det;
-            const float cn = cost(An, ln);
+            float en[TM], cn = 0.f;
+            PVD_UNROLL
+            for (int k = 0; k < TM; ++k)
+                if (k < T) {
+                    en[k] = expf(-ln * a.t[k]);
+                    const float r = a.w[k] * (y[k] - An * en[k]);
+                    cn += r * r;
+                }
             const bool ok = cn <= c;  // false for NaN
+            const float gain = c - cn, cold = c;
             if (ok) {
                 A = An;
                 lam = ln;
                 c = cn;
+                PVD_UNROLL
+                for (int k = 0; k < TM; ++k) e[k] = en[k];
             }
             mu = fminf(fmaxf(ok ? mu * 0.2f : mu * 10.f, 1e-9f), 1e9f);
+            // stop when the step no longer changes the cost or the parameters beyond float32 noise (the Newton polish
+            // below finishes the digits), or when the damping has run away without finding a descent step
+            const bool small_step = fabsf(An - A) <= 1e-5f * fabsf(A) && fabsf(ln - lam) <= 1e-5f * fabsf(lam);
+            if (fabsf(gain) <= 1e-5f * cold || (!ok && (small_step || mu >= 1e9f))) break;
         }
         float P = 0.f, Q = 0.f, h = 0.f, dh = 0.f;
         auto hfun = [&](float l, float& P_, float& Q_, float& h_, float& dh_) {
@@ -126,16 +138,17 @@ __global__ void monoexp_fit_kernel(const FitArgs a, float* __restrict__ A0out, f
         };
         hfun(lam, P, Q, h, dh);
         for (int it = 0; it < 4; ++it) {
-            const float ln = lam - (dh != 0.f ? h / dh : 0.f);
+            const float step = dh != 0.f ? h / dh : 0.f;
+            if (fabsf(step) <= 1e-7f * fabsf(lam)) break;
+            const float ln = lam - step;
             float Pn, Qn, hn, dhn;
             hfun(ln, Pn, Qn, hn, dhn);
-            if (fabsf(hn) < fabsf(h)) {
-                lam = ln;
-                P = Pn;
-                Q = Qn;
-                h = hn;
-                dh = dhn;
-            }
+            if (!(fabsf(hn) < fabsf(h))) break;
+            lam = ln;
+            P = Pn;
+            Q = Qn;
+            h = hn;
+            dh = dhn;
         }
         A = Q > 0.f ? P / Q : 0.f;
         // Ill-posed curves (e.g. activity that drops to zero after the first point) have no finite minimiser:
@@ -177,7 +190,11 @@ struct CtArgs {
     int n0, n1, n2;
     float metal_thr;  // +inf disables the fill
     float g[5];       // normalised Gaussian weights for |d| = 0..4
-    Knots knots;      // nk == 0: no density output
+    // density: rho(h) = rho0 + sum_j slope_j * clamp(h - hu_j, 0, len_j) - the piecewise-linear knot table without
+    // a data-dependent search (every lane reads the same constants; random HU would otherwise serialise the
+    // constant-bank lookups lane by lane)
+    int nseg;
+    float rho0, seg_hu[31], seg_len[31], seg_slope[31];
     int nr;
     float lo[8], hi[8];
     float* corrected;
@@ -190,51 +207,95 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // scipy 'reflect': 
     return i;
 }
 
-__global__ void ct_prepare_kernel(const CtArgs a) {
+constexpr int kCtThreads = 256;
+
+// Streaming pass, four consecutive voxels per thread (128-bit loads / stores when the volume is 16-byte aligned), no
+// block-wide synchronisation.  Metal voxels are rare, so their 9^3 gathers are not done by the owning lane alone
+// (it would run 729 taps while 31 lanes idle): the warp votes, and for every metal voxel found all 32 lanes share
+// the work - the 81 (dx, dy) columns of 9 contiguous z taps are dealt round-robin over the lanes and the partial
+// sums are combined with a butterfly of shuffles (fixed order: deterministic result).
+template <bool SEG8>  // SEG8: at most 8 density segments, padded with zero slopes -> fully unrolled, constants as operands
+__global__ void __launch_bounds__(kCtThreads) ct_prepare_kernel(const CtArgs a, const int vec) {
     const size_t n = (size_t)a.n0 * a.n1 * a.n2;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float h = a.hu[i];
-        if (h > a.metal_thr) {
-            const int z = (int)(i % a.n2);
-            const size_t r = i / a.n2;
-            const int y = (int)(r % a.n1), x = (int)(r / a.n1);
-            float acc = 0.f;
-            for (int dx = -4; dx <= 4; ++dx) {
-                const size_t ox = (size_t)reflect_idx(x + dx, a.n0) * a.n1;
-                const float gx = a.g[dx < 0 ? -dx : dx];
-                for (int dy = -4; dy <= 4; ++dy) {
-                    const size_t oy = (ox + reflect_idx(y + dy, a.n1)) * a.n2;
-                    const float gxy = gx * a.g[dy < 0 ? -dy : dy];
+    const size_t ngroups = (n + 3) / 4;
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count: every lane of a warp runs the same number of iterations (the votes need all lanes)
+    const size_t gstride = (size_t)gridDim.x * blockDim.x;
+    const size_t warp_first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    for (size_t gbase = warp_first; gbase < ngroups; gbase += gstride) {
+        const size_t i0 = 4 * (gbase + lane);
+        const bool full = vec && i0 + 4 <= n;
+        float h[4] = {0.f, 0.f, 0.f, 0.f};
+        if (full) {
+            const float4 v = *reinterpret_cast<const float4*>(a.hu + i0);
+            h[0] = v.x;
+            h[1] = v.y;
+            h[2] = v.z;
+            h[3] = v.w;
+        } else {
+            PVD_UNROLL
+            for (int q = 0; q < 4; ++q)
+                if (i0 + q < n) h[q] = a.hu[i0 + q];
+        }
+        PVD_UNROLL
+        for (int q = 0; q < 4; ++q) {
+            unsigned metal = __ballot_sync(0xFFFFFFFFu, i0 + q < n && h[q] > a.metal_thr);
+            while (metal) {
+                const int owner = __ffs(metal) - 1;
+                metal &= metal - 1;
+                const size_t iv = 4 * (gbase + owner) + q;
+                const int z = (int)(iv % a.n2);
+                const size_t r = iv / a.n2;
+                const int y = (int)(r % a.n1), x = (int)(r / a.n1);
+                int zi[9];
+                PVD_UNROLL
+                for (int d = 0; d < 9; ++d) zi[d] = reflect_idx(z + d - 4, a.n2);
+                float part = 0.f;
+                for (int col = lane; col < 81; col += 32) {
+                    const int dx = col / 9 - 4, dy = col % 9 - 4;
+                    const float* __restrict__ src = a.hu + ((size_t)reflect_idx(x + dx, a.n0) * a.n1 + reflect_idx(y + dy, a.n1)) * a.n2;
+                    float v[9];
+                    PVD_UNROLL
+                    for (int d = 0; d < 9; ++d) v[d] = __ldg(src + zi[d]);
                     float line = 0.f;
-                    for (int dz = -4; dz <= 4; ++dz) {
-                        const float v = __ldg(a.hu + oy + reflect_idx(z + dz, a.n2));
-                        line += a.g[dz < 0 ? -dz : dz] * (v > a.metal_thr ? 0.f : v);
-                    }
-                    acc += gxy * line;
+                    PVD_UNROLL
+                    for (int d = 0; d < 9; ++d) line += a.g[d < 4 ? 4 - d : d - 4] * (v[d] > a.metal_thr ? 0.f : v[d]);
+                    part += a.g[dx < 0 ? -dx : dx] * a.g[dy < 0 ? -dy : dy] * line;
                 }
+                PVD_UNROLL
+                for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, s);
+                if (lane == owner) h[q] = part;
             }
-            h = acc;
         }
-        if (a.corrected) a.corrected[i] = h;
-        if (a.rho) {
-            const Knots& k = a.knots;
-            float rr;
-            if (h <= k.hu[0]) {
-                rr = k.rho[0];
-            } else if (h >= k.hu[k.nk - 1]) {
-                rr = k.rho[k.nk - 1];
+        float rr[4];
+        unsigned lab[4];
+        PVD_UNROLL
+        for (int q = 0; q < 4; ++q) {
+            float acc = a.rho0;
+            if (SEG8) {
+                PVD_UNROLL
+                for (int j = 0; j < 8; ++j) acc = fmaf(a.seg_slope[j], fminf(fmaxf(h[q] - a.seg_hu[j], 0.f), a.seg_len[j]), acc);
             } else {
-                int j = 1;
-                while (h > k.hu[j]) ++j;
-                const float t = (h - k.hu[j - 1]) / (k.hu[j] - k.hu[j - 1]);
-                rr = k.rho[j - 1] + t * (k.rho[j] - k.rho[j - 1]);
+                for (int j = 0; j < a.nseg; ++j) acc = fmaf(a.seg_slope[j], fminf(fmaxf(h[q] - a.seg_hu[j], 0.f), a.seg_len[j]), acc);
             }
-            a.rho[i] = rr;
-        }
-        if (a.labels) {
+            rr[q] = acc;
             unsigned m = 0;
-            for (int c = 0; c < a.nr; ++c) m |= (h >= a.lo[c] && h <= a.hi[c]) ? (1u << c) : 0u;
-            a.labels[i] = (unsigned char)m;
+            PVD_UNROLL
+            for (int c = 0; c < 8; ++c) m |= (h[q] >= a.lo[c] && h[q] <= a.hi[c]) ? (1u << c) : 0u;  // unused ranges are empty (lo > hi)
+            lab[q] = m;
+        }
+        if (full) {
+            if (a.corrected) *reinterpret_cast<float4*>(a.corrected + i0) = make_float4(h[0], h[1], h[2], h[3]);
+            if (a.rho) *reinterpret_cast<float4*>(a.rho + i0) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+            if (a.labels) *reinterpret_cast<unsigned*>(a.labels + i0) = lab[0] | (lab[1] << 8) | (lab[2] << 16) | (lab[3] << 24);
+        } else {
+            PVD_UNROLL
+            for (int q = 0; q < 4; ++q)
+                if (i0 + q < n) {
+                    if (a.corrected) a.corrected[i0 + q] = h[q];
+                    if (a.rho) a.rho[i0 + q] = rr[q];
+                    if (a.labels) a.labels[i0 + q] = (unsigned char)lab[q];
+                }
         }
     }
 }
@@ -256,8 +317,25 @@ struct RoiStats {
     unsigned long long count;
 };
 
+// four mask values at once: a 32-bit word of uint8 flags or a float4
+__device__ __forceinline__ void load_mask4(const unsigned char* m, size_t i4, bool in[4]) {
+    const unsigned u = reinterpret_cast<const unsigned*>(m)[i4];
+    in[0] = (u & 0xFFu) != 0;
+    in[1] = (u & 0xFF00u) != 0;
+    in[2] = (u & 0xFF0000u) != 0;
+    in[3] = (u & 0xFF000000u) != 0;
+}
+__device__ __forceinline__ void load_mask4(const float* m, size_t i4, bool in[4]) {
+    const float4 v = reinterpret_cast<const float4*>(m)[i4];
+    in[0] = v.x > 0.f;
+    in[1] = v.y > 0.f;
+    in[2] = v.z > 0.f;
+    in[3] = v.w > 0.f;
+}
+
+// n4 = number of 4-voxel groups read with 128-bit loads (0 when the arrays are not aligned); the rest is scalar.
 template <class M>
-__global__ void roi_minmax_kernel(const float* __restrict__ dose, const M* __restrict__ mask, size_t n, RoiStats* out) {
+__global__ void roi_minmax_kernel(const float* __restrict__ dose, const M* __restrict__ mask, size_t n, size_t n4, RoiStats* out) {
     __shared__ unsigned s_min, s_max;
     __shared__ unsigned long long s_cnt;
     if (threadIdx.x == 0) {
@@ -268,14 +346,24 @@ __global__ void roi_minmax_kernel(const float* __restrict__ dose, const M* __res
     __syncthreads();
     unsigned lo = 0xFFFFFFFFu, hi = 0u;
     unsigned long long cnt = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (mask[i] > (M)0) {
-            const unsigned k = f2key(dose[i]);
-            lo = k < lo ? k : lo;
-            hi = k > hi ? k : hi;
-            ++cnt;
-        }
+    auto take = [&](float d) {
+        const unsigned k = f2key(d);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+        ++cnt;
+    };
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = gtid; i < n4; i += stride) {
+        const float4 d = reinterpret_cast<const float4*>(dose)[i];
+        bool in[4];
+        load_mask4(mask, i, in);
+        if (in[0]) take(d.x);
+        if (in[1]) take(d.y);
+        if (in[2]) take(d.z);
+        if (in[3]) take(d.w);
     }
+    for (size_t i = 4 * n4 + gtid; i < n; i += stride)
+        if (mask[i] > (M)0) take(dose[i]);
     if (cnt) {
         atomicMin(&s_min, lo);
         atomicMax(&s_max, hi);
@@ -292,7 +380,7 @@ __global__ void roi_minmax_kernel(const float* __restrict__ dose, const M* __res
 constexpr int kDvhSmemBins = 4096;
 
 template <class M>
-__global__ void dvh_hist_kernel(const float* __restrict__ dose, const M* __restrict__ mask, size_t n,
+__global__ void dvh_hist_kernel(const float* __restrict__ dose, const M* __restrict__ mask, size_t n, size_t n4,
                                 const float* __restrict__ edges, int bins, float first, float last,
                                 unsigned long long* __restrict__ hist) {
     __shared__ unsigned s_hist[kDvhSmemBins];
@@ -302,17 +390,27 @@ __global__ void dvh_hist_kernel(const float* __restrict__ dose, const M* __restr
         __syncthreads();
     }
     const float denom = __fsub_rn(last, first);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (!(mask[i] > (M)0)) continue;
-        const float x = dose[i];
-        if (!(x >= first && x <= last)) continue;  // NaN doses are dropped, as numpy's `keep` mask does
+    auto take = [&](float x) {
+        if (!(x >= first && x <= last)) return;  // NaN doses are dropped, as numpy's `keep` mask does
         int idx = (int)__fmul_rn(__fdiv_rn(__fsub_rn(x, first), denom), (float)bins);
         if (idx == bins) --idx;
         if (x < edges[idx]) --idx;
         else if (idx != bins - 1 && x >= edges[idx + 1]) ++idx;
         if (use_smem) atomicAdd(&s_hist[idx], 1u);
         else atomicAdd(&hist[idx], 1ull);
+    };
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = gtid; i < n4; i += stride) {
+        const float4 d = reinterpret_cast<const float4*>(dose)[i];
+        bool in[4];
+        load_mask4(mask, i, in);
+        if (in[0]) take(d.x);
+        if (in[1]) take(d.y);
+        if (in[2]) take(d.z);
+        if (in[3]) take(d.w);
     }
+    for (size_t i = 4 * n4 + gtid; i < n; i += stride)
+        if (mask[i] > (M)0) take(dose[i]);
     if (use_smem) {
         __syncthreads();
         for (int b = threadIdx.x; b < bins; b += blockDim.x)

@@ -180,8 +180,8 @@ struct LastStage {
 // ------------------------------------------------------------------------------------------------
 // Column passes (axis 1 forward / inverse, axis 0 forward * spectrum * inverse, kernel spectrum).
 // One tile per CTA; used where the double-buffered persistent variant (fft_pipe.cuh) does not fit.
-template <int N, int NT, int R1, int R2, int R3, int MODE>
-__global__ void __launch_bounds__(NT) cols_fast_kernel(const ColArgs g) {
+template <int N, int NT, int R1, int R2, int R3, int MODE, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
     constexpr int W = 16;
     using LS_ = LastStage<N, NT, R1, R2, R3>;
     constexpr int RL = LS_::RL, TPC = LS_::TPC, BPTL = LS_::BPT;

@@ -14,8 +14,10 @@
 
 #ifdef PVD_EMULATE
 // ------------------------------------------------------------------ CPU emulation of SIMT
+#include <algorithm>
 #include <barrier>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 #include <cstdlib>
@@ -42,6 +44,9 @@ struct Ctx {
     dim3 tid, bid, bdim, gdim;
     std::barrier<>* bar = nullptr;
     char* smem = nullptr;
+    std::barrier<>* warp_bar = nullptr;  // the 32 (or fewer) threads of this thread's warp
+    unsigned* warp_buf = nullptr;        // 32-word exchange buffer of the warp (ballot / shuffle emulation)
+    unsigned lane = 0, warp_lanes = 32;
 };
 inline thread_local Ctx ctx;
 }  // namespace pvd_emu
@@ -50,6 +55,40 @@ inline thread_local Ctx ctx;
 #define blockDim (pvd_emu::ctx.bdim)
 #define gridDim (pvd_emu::ctx.gdim)
 static inline void __syncthreads() { pvd_emu::ctx.bar->arrive_and_wait(); }
+// Warp-level primitives (full-mask, convergent use only): every lane publishes its word, the warp meets, reads, meets.
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { pvd_emu::ctx.warp_bar->arrive_and_wait(); }
+static inline unsigned pvd_emu_exchange(unsigned mine, unsigned src_lane) {
+    pvd_emu::Ctx& c = pvd_emu::ctx;
+    c.warp_buf[c.lane] = mine;
+    c.warp_bar->arrive_and_wait();
+    const unsigned v = c.warp_buf[src_lane < c.warp_lanes ? src_lane : c.lane];
+    c.warp_bar->arrive_and_wait();
+    return v;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    pvd_emu::Ctx& c = pvd_emu::ctx;
+    c.warp_buf[c.lane] = pred ? 1u : 0u;
+    c.warp_bar->arrive_and_wait();
+    unsigned m = 0;
+    for (unsigned l = 0; l < c.warp_lanes; ++l) m |= c.warp_buf[l] << l;
+    c.warp_bar->arrive_and_wait();
+    return m;
+}
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+    unsigned u;
+    std::memcpy(&u, &v, 4);
+    u = pvd_emu_exchange(u, pvd_emu::ctx.lane ^ (unsigned)lane_mask);
+    std::memcpy(&v, &u, 4);
+    return v;
+}
+static inline float __shfl_sync(unsigned, float v, int src) {
+    unsigned u;
+    std::memcpy(&u, &v, 4);
+    u = pvd_emu_exchange(u, (unsigned)src);
+    std::memcpy(&v, &u, 4);
+    return v;
+}
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
@@ -86,12 +125,20 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
     const unsigned T = block.x * block.y * block.z;
     std::vector<char> smem(smem_bytes + 64);
     std::barrier<> bar((std::ptrdiff_t)T);
+    const unsigned nwarps = (T + 31) / 32;
+    std::vector<std::unique_ptr<std::barrier<>>> wbars;
+    for (unsigned w = 0; w < nwarps; ++w) wbars.emplace_back(new std::barrier<>((std::ptrdiff_t)std::min(32u, T - 32 * w)));
+    std::vector<unsigned> wbuf(32 * nwarps);
     auto worker = [&](unsigned t) {
         Ctx& c = ctx;
         c.bdim = block;
         c.gdim = grid;
         c.bar = &bar;
         c.smem = smem.data();
+        c.warp_bar = wbars[t / 32].get();
+        c.warp_buf = wbuf.data() + 32 * (t / 32);
+        c.lane = t % 32;
+        c.warp_lanes = std::min(32u, T - 32 * (t / 32));
         c.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
         for (unsigned bz = 0; bz < grid.z; ++bz)
             for (unsigned by = 0; by < grid.y; ++by)

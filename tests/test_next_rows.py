@@ -200,6 +200,22 @@ def test_emulated_ct_prepare_vs_reference_vectors(emu, gold):
         emu.ct_prepare(hu.ctypes.data, hu.shape, 2000.0 if handle else float("inf"), orc.HU_KNOTS.tolist(), _ranges(),
                        corrected.ctypes.data, rho.ctypes.data, labels.ctypes.data)
         _check_ct(gold, corrected, rho, labels, handle)
+    # a volume that is only 4-byte aligned takes the scalar load/store path
+    buf = np.zeros(hu.size + 1, np.float32)
+    hu_off = buf[1:].reshape(hu.shape)
+    hu_off[...] = hu
+    assert hu_off.ctypes.data % 16 == 4 or hu_off.ctypes.data % 16 != 0
+    c2 = np.empty_like(hu)
+    l2 = np.empty(hu.shape, np.uint8)
+    emu.ct_prepare(hu_off.ctypes.data, hu.shape, 2000.0, None, _ranges(), c2.ctypes.data, None, l2.ctypes.data)
+    emu.ct_prepare(hu.ctypes.data, hu.shape, 2000.0, None, _ranges(), corrected.ctypes.data, None, labels.ctypes.data)
+    assert np.array_equal(c2, corrected) and np.array_equal(l2, labels)
+    # more than 8 density segments -> the generic (loop) variant; must equal np.interp with clamped ends
+    knots12 = [(-1000.0 + 300.0 * j, 0.001 + 0.21 * j + 0.01 * j * j) for j in range(12)]
+    r12 = np.empty_like(hu)
+    emu.ct_prepare(hu.ctypes.data, hu.shape, float("inf"), knots12, None, None, r12.ctypes.data, None)
+    kx, ky = np.array(knots12).T
+    np.testing.assert_allclose(r12, np.interp(hu.astype(np.float64), kx, ky), rtol=3e-6)
     # tiny volume: reflections longer than the axis
     t = np.full((2, 1, 3), 100.0, np.float32)
     t[0, 0, 1] = 2500.0
@@ -248,6 +264,15 @@ def test_emulated_dvh_vs_reference_vectors(emu, gold):
         emu.dvh_histogram(dose.ctypes.data, maskf.ctypes.data, True, dose.size, edges.ctypes.data, bins, float(edges[0]), float(edges[-1]),
                           hist.ctypes.data)
         np.testing.assert_array_equal(hist, np.histogram(sel, bins=bins)[0])
+    # 4-byte aligned views: scalar path, same counts
+    d1, m1 = dose.ravel()[1:], np.ascontiguousarray(maskf.ravel()[1:] > 0).view(np.uint8)
+    mn, mx, cnt = emu.roi_minmax(d1.ctypes.data, m1.ctypes.data, False, d1.size, scratch.ctypes.data)
+    sel1 = d1[m1 > 0]
+    assert d1.ctypes.data % 16 != 0 and (mn, mx, cnt) == (sel1.min(), sel1.max(), sel1.size)
+    edges = np.histogram_bin_edges(np.array([mn, mx], np.float32), bins=7)
+    hist = np.empty(7, np.uint64)
+    emu.dvh_histogram(d1.ctypes.data, m1.ctypes.data, False, d1.size, edges.ctypes.data, 7, float(edges[0]), float(edges[-1]), hist.ctypes.data)
+    np.testing.assert_array_equal(hist, np.histogram(sel1, bins=7)[0])
     const = np.full(10, 7.0, np.float32)
     ones = np.ones(10, np.uint8)
     edges = np.histogram_bin_edges(const, bins=4)

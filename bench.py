@@ -415,7 +415,7 @@ def run_sharded(args, wl, name):
     from pyvoxeldosimetry_b200.engine import ConvPlan
     from pyvoxeldosimetry_b200.multi_gpu import SlabConvolver, shard_range
 
-    boundary = args.boundary if name == "c4" else "same"
+    boundary = args.boundary
     calc = KernelConvolutionCalculator(wl["nuclide"], "water", wl["voxel"], config={"kernel_grid": wl["kgrid"], "boundary": boundary, "device": str(dev)})
     kdev = calc._kernel_dev
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -481,9 +481,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--boundary", default="reference", choices=["reference", "same"])
+    ap.add_argument("--boundary", default=None, choices=["reference", "same"],
+                    help="default: reference (the reference's circular semantics); c5 defaults to same (zero boundary)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.boundary is None:
+        args.boundary = "same" if args.workload == "c5" else "reference"
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)

@@ -69,6 +69,9 @@ const char* pvd_last_error(void);
 
 /* Smallest transform length >= n the engine handles efficiently ({2,3,5,7}-smooth, few radix stages). */
 int pvd_good_fft_size(int n);
+/* Same for a given axis (0, 1: strided column passes, 2: contiguous row passes - they have different menus of
+ * size-specialised kernels). */
+int pvd_good_fft_size_axis(int n, int axis);
 
 /* ---- A1: KernelConvolutionCalculator.calculate_dose_rate (core/kernel_convolution.py:48-76) ----
  * Plan for convolving [n0][n1][n2] activity volumes with a [k0][k1][k2] dose voxel kernel. */

@@ -21,7 +21,7 @@ MAX_T = 16
 
 # every symbol include/pvdose.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "pvd_version", "pvd_last_error", "pvd_good_fft_size", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
+    "pvd_version", "pvd_last_error", "pvd_good_fft_size", "pvd_good_fft_size_axis", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
     "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times",
     "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
     "pvd_density_scale", "pvd_monoexp_fit", "pvd_ct_prepare", "pvd_roi_minmax", "pvd_dvh_histogram",
@@ -74,6 +74,7 @@ class PvdLib:
         d.pvd_version.restype = C.c_int
         d.pvd_last_error.restype = C.c_char_p
         d.pvd_good_fft_size.argtypes = [C.c_int]
+        d.pvd_good_fft_size_axis.argtypes = [C.c_int, C.c_int]
         d.pvd_plan_create.argtypes = [C.POINTER(vp), ip, ip, C.c_int, C.c_int]
         d.pvd_plan_create_ex.argtypes = [C.POINTER(vp), ip, ip, ip, ip, ip, C.c_int]
         d.pvd_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
@@ -103,8 +104,8 @@ class PvdLib:
     def version(self) -> int:
         return self.dll.pvd_version()
 
-    def good_fft_size(self, n: int) -> int:
-        return self.dll.pvd_good_fft_size(int(n))
+    def good_fft_size(self, n: int, axis: int = 0) -> int:
+        return self.dll.pvd_good_fft_size_axis(int(n), int(axis))
 
     def plan_create(self, n, k, boundary: int, algo: int = ALGO_AUTO) -> int:
         h = C.c_void_p()

@@ -284,11 +284,13 @@ __global__ void __launch_bounds__(NT) rows_fwd_fast_kernel(const RowFwdArgs g) {
             float acc[ZIT];
             PVD_UNROLL
             for (int i = 0; i < ZIT; ++i) acc[i] = 0.f;
+            // TB time points per batch (TB * ZIT independent loads in flight per lane, bounded by the register budget)
+            constexpr int TB = ZIT <= 8 ? 4 : (ZIT <= 16 ? 2 : 1);
             int t = 0;
-            for (; t + 4 <= T; t += 4) {  // four time points per batch: 4 * ZIT independent loads in flight per lane
-                float v[4][ZIT];
+            for (; TB > 1 && t + TB <= T; t += TB) {
+                float v[TB][ZIT];
                 PVD_UNROLL
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < TB; ++q) {
                     const float* __restrict__ pt = g.in[t + q] + off;
                     PVD_UNROLL
                     for (int i = 0; i < ZIT; ++i) {
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(NT) rows_fwd_fast_kernel(const RowFwdArgs g) {
                     }
                 }
                 PVD_UNROLL
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < TB; ++q) {
                     const float wt = g.w[t + q];
                     PVD_UNROLL
                     for (int i = 0; i < ZIT; ++i) acc[i] = fmaf(wt, v[q][i], acc[i]);

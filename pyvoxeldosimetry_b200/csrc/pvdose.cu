@@ -182,6 +182,8 @@ struct FastRows {
             rows_fwd_pipe_kernel<N, NT, MINB, R1, R2, R3>, rows_inv_pipe_kernel<N, NT, MINB, R1, R2, R3>,  \
             (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES + Sched<N, R1, R2, R3>::TOTAL * sizeof(float2) \
     }
+#define PVD_ROWS_NOPIPE(N, NT, R1, R2, R3) \
+    { N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>, nullptr, nullptr, 0 }
 const FastCols kFastCols[] = {
     PVD_COLS_CX(512, 512, 1, 8, 8, 8, 256, 2, 16, 32, 1),
     PVD_COLS(256, 256, 2, 16, 16, 1),
@@ -190,6 +192,11 @@ const FastCols kFastCols[] = {
     PVD_COLS(432, 384, 1, 18, 24, 1),
     PVD_COLS(288, 288, 2, 16, 18, 1),   // 256 + kernel reach
     PVD_COLS_NOPIPE(1024, 1024, 16, 8, 8),
+    // slab decomposition of the 1024 x 1024 x 800 volume ('same' mode): 1024 + reach -> 1152, slabs of
+    // 256 / 128 planes + 50 halo planes -> 320 / 192
+    PVD_COLS_NOPIPE(1152, 768, 8, 12, 12),
+    PVD_COLS(320, 320, 2, 16, 20, 1),
+    PVD_COLS(192, 256, 3, 12, 16, 1),
 };
 const FastRows kFastRows[] = {
     PVD_ROWS(400, 320, 2, 20, 20, 1),
@@ -197,6 +204,8 @@ const FastRows kFastRows[] = {
     PVD_ROWS(512, 512, 1, 8, 8, 8),
     PVD_ROWS(432, 384, 1, 18, 24, 1),   // 400 + kernel reach
     PVD_ROWS(288, 288, 2, 16, 18, 1),
+    PVD_ROWS(800, 640, 1, 8, 10, 10),          // 1024 x 1024 x 800, reference mode
+    PVD_ROWS_NOPIPE(864, 576, 8, 9, 12),       // 800 + kernel reach (tile + staging buffer exceed one SM's shared memory)
 };
 const FastCols* find_fast_cols(int n) {
     for (const auto& e : kFastCols)
@@ -532,6 +541,7 @@ extern "C" {
 int pvd_version(void) { return PVD_VERSION; }
 const char* pvd_last_error(void) { return g_err.c_str(); }
 int pvd_good_fft_size(int n) { return good_size_axis(n, 0); }
+int pvd_good_fft_size_axis(int n, int axis) { return good_size_axis(n, axis == 2 ? 2 : 0); }
 
 int pvd_plan_create_ex(pvd_plan** out, const int n[3], const int m[3], const int out_lo[3], const int out_n[3],
                        const int k[3], int algo) {
@@ -646,7 +656,7 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
             }
     if (p->fastRows && (PVD_SET_SMEM(p->fastRows->fwd, kMaxSmem) != 0 || PVD_SET_SMEM(p->fastRows->inv, kMaxSmem) != 0))
         return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (rows)");
-    if (p->fastRows && p->fastRows->smemPipe <= kMaxSmem) {
+    if (p->fastRows && p->fastRows->fwdPipe && p->fastRows->smemPipe <= kMaxSmem) {
         const FastRows* f = p->fastRows;
         if (PVD_SET_SMEM(f->fwdPipe, kMaxSmem) != 0 || PVD_SET_SMEM(f->invPipe, kMaxSmem) != 0)
             return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (rows pipe)");

@@ -27,12 +27,12 @@ def slab_bounds(n0: int, world: int) -> List[Tuple[int, int]]:
     return [(r.start, r.stop) for r in (shard_range(n0, world, k) for k in range(world))]
 
 
-def good_size_py(n: int, lib=None) -> int:
+def good_size_py(n: int, lib=None, axis: int = 0) -> int:
     if lib is not None:
-        return lib.good_fft_size(n)
+        return lib.good_fft_size(n, axis)
     from ._capi import get_lib
 
-    return get_lib().good_fft_size(n)
+    return get_lib().good_fft_size(n, axis)
 
 
 def slab_geometry(shape: Sequence[int], kshape: Sequence[int], boundary: str, world: int, rank: int, lib=None) -> Dict:
@@ -61,8 +61,8 @@ def slab_geometry(shape: Sequence[int], kshape: Sequence[int], boundary: str, wo
         dn = k0 - 1 - c[0]
         L = B + k0 - 1
         m = [good_size_py(L, lib)]
-        for n, k, cc in ((n1, k1, c[1]), (n2, k2, c[2])):
-            m.append(good_size_py(max(n + k - 1 - cc, k, n + cc), lib))
+        for axis, (n, k, cc) in enumerate(((n1, k1, c[1]), (n2, k2, c[2])), start=1):
+            m.append(good_size_py(max(n + k - 1 - cc, k, n + cc), lib, axis))
         return dict(lo=lo, hi=hi, need_lo=lo - dn, need_hi=hi + c[0], kcrop=(k0, k1, k2), n=(L, n1, n2),
                     ex=dict(m=tuple(m), out_lo=(k0 - 1, c[1], c[2]), out_n=(B, n1, n2)))
     raise ValueError(f"unknown boundary mode {boundary!r}")

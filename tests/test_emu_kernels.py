@@ -187,6 +187,11 @@ FAST_CASES = [
     ((4, 33, 376), (1, 3, 41), 1, 1, True),    # same mode: 376 -> 400 partial cp.async zero fill
     ((3, 35, 379), (1, 3, 41), 1, 1, True),    # n2 % 4 != 0 -> unaligned rows fall back to the LDG kernel
     ((500, 2, 4), (25, 1, 3), 1, 1, False),    # same mode along x: 500 -> 512, crop offset 12
+    ((1152, 2, 4), (5, 1, 2), 0, 1, True),     # slab-decomposition sizes: x <1152> 8*12*12 (one tile per CTA)
+    ((2, 320, 6), (1, 7, 2), 0, 1, False),     # y <320> 16*20
+    ((192, 3, 4), (9, 2, 1), 0, 2, True),      # x <192> 12*16 (guarded second stage)
+    ((3, 5, 800), (2, 2, 9), 0, 1, True),      # rows <800> 8*10*10, pipelined, one CTA per SM
+    ((2, 6, 840), (1, 3, 25), 1, 1, True),     # rows <864> 8*9*12: same mode 840 -> 864, no staging pipeline
 ]
 
 

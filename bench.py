@@ -133,6 +133,33 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(local: int) -> str:
+    """One rank per GPU: run this rank's host threads (and so its pinned staging buffers, first touch) on the CPUs
+    of the GPU's own NUMA node, so that host<->device copies of different ranks do not share one socket's memory
+    controllers / inter-socket link.  Best effort; returns a note for stderr."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"rank on GPU {local} ({bdf}) bound to {len(cpus)} local CPUs ({spec})"
+        return f"GPU {local} ({bdf}): no usable local CPUs in {spec!r}"
+    except Exception as e:  # sysfs layout / permissions differ: keep the default affinity
+        return f"NUMA binding skipped: {e}"
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -234,6 +261,7 @@ def run_ours(args, wl):
     dev = torch.device(f"cuda:{local}")
     dist = None
     if world > 1:
+        sys.stderr.write(bind_to_gpu_numa(local) + "\n")
         import torch.distributed as dist_mod
 
         dist = dist_mod
@@ -359,7 +387,7 @@ def run_ours(args, wl):
         dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
         traffic = None  # dram__bytes_read+write of the whole path from the committed ncu --set full capture (same workload only)
-        tpath = os.path.join(REPO, "profiles", "r01_dram_traffic_c3.json")
+        tpath = os.path.join(REPO, "profiles", "r01d_dram_traffic_c3.json")
         if args.workload == "c3" and args.boundary == "reference" and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("_whole_path_dram_bytes")
         line = {

@@ -57,6 +57,13 @@ __device__ __forceinline__ float2 ldg64_ro(const float2* p) {  // data that is r
     return v;
 #endif
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef PVD_EMULATE
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 __device__ __forceinline__ void stg64(float2* p, float2 v) {
 #ifdef PVD_EMULATE
     *p = v;
@@ -223,6 +230,19 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
     } else if constexpr (MODE == COL_INV) {
         fast_fft<N, W, W, NT, +1, R1, R2, R3, false, false>(gin, gout, tile, tws);
     } else {  // COL_CONV: forward -> * spectrum -> inverse, the middle never leaves registers
+        // L2 prefetch (no registers held): the spectrum lines this CTA multiplies by after its forward transform, and
+        // the input lines of the tile that the CTA scheduled into this slot next will most likely get (blocks are
+        // dispatched in linear order, pf_dist = CTAs resident on the whole GPU) - their first-stage loads then hit L2.
+        if (g.pf_dist > 0) {
+            const float2* sp0 = g.spec + base;
+            for (int r = threadIdx.x; r < g.M; r += NT) prefetch_l2(sp0 + (size_t)r * es);
+            const long long nxt = (long long)blockIdx.y * gridDim.x + blockIdx.x + g.pf_dist;
+            const long long ny = nxt / gridDim.x, nx = nxt - ny * gridDim.x;
+            if (ny < gridDim.y) {
+                const float2* in0 = g.in + (long long)(g.outer0 + (int)ny) * g.os + nx * W;
+                for (int r = threadIdx.x; r < n_in; r += NT) prefetch_l2(in0 + (size_t)r * es);
+            }
+        }
         float2 hold[BPTL][RL];
         auto rout = [&](int u, int k, int, int, float2 v) { hold[u][k] = v; };
         fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, rout, tile, tws);

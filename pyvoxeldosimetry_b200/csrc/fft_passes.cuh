@@ -93,6 +93,7 @@ struct ColArgs {
     int Wlog;           // tile width 2^Wlog frequencies
     int mode;
     float scale;
+    int pf_dist;  // one-tile-per-CTA kernels: L2-prefetch the tile of block (linear id + pf_dist); 0 = off
     const float2* tw;
     Stages st;
 };

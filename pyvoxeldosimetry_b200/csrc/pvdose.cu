@@ -249,6 +249,7 @@ struct pvd_plan {
     bool usePipe = true;
     int pipeGrid[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // persistent grid size per axis / mode
     int rowPipeGrid[2] = {0, 0};                        // persistent grid size of the row passes (fwd, inv)
+    int fnGrid[2] = {0, 0};                             // CTAs of the one-tile-per-CTA CONV kernel resident on the GPU
     // direct (TMA) path
     int want_algo = PVD_ALGO_AUTO;
     int dbox[3] = {0, 0, 0};
@@ -368,6 +369,10 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
     if (p->fastCols[axis]) {
         const FastCols* f = p->fastCols[axis];
         const size_t smem = ((size_t)f->N * 16 + 4 * f->N) * sizeof(float2);
+        if (mode == COL_CONV) {
+            const char* e = getenv("PVD_PF_DIST");  // experiment knob; default = one resident wave
+            a.pf_dist = e ? atoi(e) : p->fnGrid[axis];
+        }
         PVD_LAUNCH(f->fn[mode], dim3((unsigned)((p->Nh + 15) / 16), (unsigned)nouter), dim3(f->fnNT[mode]), smem, stream, a);
         PVD_CUDA_CHECK("cols_fast_kernel");
         return PVD_OK;
@@ -645,6 +650,13 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
             {
                 const FastCols* f = p->fastCols[a];
                 if (PVD_SET_SMEM(f->fn[md], kMaxSmem) != 0) return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (cols)");
+                if (md == COL_CONV) {
+                    int dev = 0, sms = 0, per = 0;
+                    cudaGetDevice(&dev);
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->fn[md], f->fnNT[md], ((size_t)f->N * 16 + 4 * f->N) * sizeof(float2));
+                    p->fnGrid[a] = sms * per;
+                }
                 if (f->pipe[md]) {
                     if (PVD_SET_SMEM(f->pipe[md], kMaxSmem) != 0) return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (pipe)");
                     int dev = 0, sms = 0, per = 0;

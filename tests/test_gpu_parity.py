@@ -173,3 +173,46 @@ def test_direct_tma_conv_matches_oracle(torch_cuda, shape, kshape):
     out = plan.execute([torch.from_numpy(a).to(dev), torch.from_numpy(a).to(dev)], [0.25, 0.5]).cpu().numpy()
     plan.close()
     assert orc.rel_err_of_peak(out, 0.75 * orc.conv_same(a.astype(np.float64), k.astype(np.float64), fast=True)) <= TOL
+
+
+def test_c3_full_size_vs_oracle(torch_cuda):
+    """Config C3 at its full size: 512x512x400 Y90 volume, 51^3 kernel, density-corrected, reference boundary mode,
+    against the float64 oracle (scipy real transforms with all host threads: same mathematics as the literal
+    np.fft expression, SURVEY section 8d "Baseline B")."""
+    rng = np.random.default_rng(90)
+    shape = (512, 512, 400)
+    a = rng.uniform(0.0, 1e2, shape).astype(np.float32)
+    a[200:300, 220:330, 150:260] = 2e6
+    x = (np.arange(512, dtype=np.float32) - 256) / 215.0
+    body = (x[:, None] ** 2 + (x[None, :] * 1.4) ** 2) <= 1.0
+    plane = np.where(body, 1.04, 0.00129).astype(np.float32)
+    plane[(np.abs(x[:, None] - 0.45) < 0.25) & (np.abs(x[None, :]) < 0.3)] = 0.26
+    rho = np.ascontiguousarray(np.broadcast_to(plane[:, :, None], shape))
+    k = orc.y90_kernel(1.0, (51, 51, 51), "water")
+    got = run_plan(torch_cuda, [a], k, "reference", density=rho)
+    ref = orc.conv_reference_fast(a.astype(np.float64), k.astype(np.float32).astype(np.float64))
+    ref = orc.density_correct(ref, rho.astype(np.float64))
+    assert orc.rel_err_of_peak(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("shape,boundary,fft_shape", [
+    ((40, 1030, 830), "same", (None, 1152, 864)),      # slab sizes of the 1024x1024x800 volume: columns <1152>, rows <864>
+    ((24, 1024, 800), "reference", (24, 1024, 800)),   # reference mode: columns <1024>, rows <800>
+    ((270, 64, 100), "same", (320, None, None)),       # 256-plane slab + halo -> <320>
+    ((150, 48, 60), "same", (192, None, None)),        # 128-plane slab + halo -> <192>
+])
+def test_slab_menu_sizes_vs_oracle(torch_cuda, shape, boundary, fft_shape):
+    from pyvoxeldosimetry_b200.engine import ConvPlan
+
+    rng = np.random.default_rng(5)
+    a = rng.uniform(0.0, 1e3, shape).astype(np.float32)
+    a[tuple(s // 2 for s in shape)] = 2e6
+    k = orc.y90_kernel(1.0, (51, 51, 51), "water") if shape[0] >= 150 else orc.y90_kernel(1.0, (25, 51, 51), "water")
+    plan = ConvPlan(shape, k.shape, boundary, "cuda:0")
+    for got_m, want in zip(plan.fft_shape, fft_shape):
+        assert want is None or got_m == want, (plan.fft_shape, fft_shape)
+    plan.close()
+    got = run_plan(torch_cuda, [a], k, boundary)
+    k32 = k.astype(np.float32).astype(np.float64)
+    ref = orc.conv_reference_fast(a.astype(np.float64), k32) if boundary == "reference" else orc.conv_same(a.astype(np.float64), k32, fast=True)
+    assert orc.rel_err_of_peak(got, ref) <= TOL

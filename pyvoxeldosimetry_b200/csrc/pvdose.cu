@@ -370,8 +370,10 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
         const FastCols* f = p->fastCols[axis];
         const size_t smem = ((size_t)f->N * 16 + 4 * f->N) * sizeof(float2);
         if (mode == COL_CONV) {
-            const char* e = getenv("PVD_PF_DIST");  // experiment knob; default = one resident wave
-            a.pf_dist = e ? atoi(e) : p->fnGrid[axis];
+            // experiment knob, off by default: L2-prefetching the spectrum lines and the tile of block id + pf_dist
+            // measured SLOWER on the B200 (P3 0.272 ms off, 0.290 / 0.309 / 0.318 / 0.336 ms for 2 / 148 / 296 / 592)
+            const char* e = getenv("PVD_PF_DIST");
+            a.pf_dist = e ? atoi(e) : 0;
         }
         PVD_LAUNCH(f->fn[mode], dim3((unsigned)((p->Nh + 15) / 16), (unsigned)nouter), dim3(f->fnNT[mode]), smem, stream, a);
         PVD_CUDA_CHECK("cols_fast_kernel");

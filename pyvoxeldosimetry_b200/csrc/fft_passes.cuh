@@ -154,6 +154,7 @@ struct RowInvArgs {
     int M2, Nh;
     int Llog;
     int vec4;  // pipelined kernel: dose/density rows are 16-byte aligned and O2 % 4 == 0 -> 128-bit store phase
+    int den_pf;  // pipelined kernel: L2-prefetch a tile's density rows before its inverse transform
     const float2* tw;
     Stages st;
 };

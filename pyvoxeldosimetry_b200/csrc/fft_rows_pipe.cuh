@@ -154,9 +154,20 @@ __device__ __forceinline__ void stg128(float* p, float4 v) {
 }
 #endif
 
+// 1/x as ONE MUFU.RCP (rcp.approx.ftz, 1 ulp): __fdividef wraps it in a denormal-rescaling sequence (5 more
+// instructions per voxel) that max(rho, rho_min) never needs
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifdef PVD_EMULATE
+    return 1.0f / x;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
 // dose = v * sr / max(rho, rho_min), zero below rho_cut   (sr = scale * rho_ref)
 __device__ __forceinline__ float den_apply(float v, float rho, float sr, float rho_min, float rho_cut) {
-    const float f = v * __fdividef(sr, fmaxf(rho, rho_min));
+    const float f = v * (sr * fast_rcp(fmaxf(rho, rho_min)));
     return (rho < rho_cut) ? 0.f : f;
 }
 
@@ -246,6 +257,21 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
         const int tn = t + gridDim.x;
         if (tn < ntiles) issue_spec(tn);
         cp_async_commit();
+        if (has_den && g.den_pf) {
+            // the density rows of THIS tile are needed after the inverse transform (~10 us from now): pull their
+            // 128-byte lines into L2 now so that the store phase does not wait a full DRAM round trip per row
+            const int r0 = t * 32;
+            const int px0 = r0 / O1, py0 = r0 - px0 * O1;
+            const int lines_per_row = (O2 * 4 + 127) / 128;
+            for (int i = threadIdx.x; i < 32 * lines_per_row; i += NT) {
+                const int rr = i / lines_per_row, ln = i - rr * lines_per_row;
+                if (r0 + rr < (int)nrows) {
+                    int x, y;
+                    row_xy(px0, py0, rr, x, y);
+                    prefetch_l2(g.density + x * g.den_s0 + y * g.den_s1 + ln * 32);
+                }
+            }
+        }
         auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
         float* rowA = rowbuf + wl * LSA - z_lo;
         auto row_out = [&](int, int, int idx, int, float2 v) {

@@ -777,6 +777,10 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     a.Llog = p->rowLlog;
     a.tw = p->tw(2);
     a.st = p->st[2];
+    {
+        const char* e = getenv("PVD_DEN_PF");  // experiment knob
+        a.den_pf = e ? atoi(e) : 1;
+    }
     a.vec4 = (p->on[2] % 4 == 0 && a.out_s0 % 4 == 0 && a.out_s1 % 4 == 0 && ((uintptr_t)dose & 15) == 0 &&
               (!density || (((uintptr_t)density & 15) == 0 && a.den_s0 % 4 == 0 && a.den_s1 % 4 == 0)))
                  ? 1

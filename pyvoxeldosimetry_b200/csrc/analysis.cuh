@@ -24,11 +24,6 @@ static inline unsigned atomicMax(unsigned* p, unsigned v) {
     }
     return old;
 }
-static inline unsigned __float_as_uint(float f) {
-    unsigned u;
-    std::memcpy(&u, &f, 4);
-    return u;
-}
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

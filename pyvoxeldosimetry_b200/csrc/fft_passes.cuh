@@ -155,6 +155,7 @@ struct RowInvArgs {
     int Llog;
     int vec4;  // pipelined kernel: dose/density rows are 16-byte aligned and O2 % 4 == 0 -> 128-bit store phase
     int den_pf;  // pipelined kernel: L2-prefetch a tile's density rows before its inverse transform
+    int zero;    // always 0 (the struct is memset): an operand the compiler cannot fold, see the P5 store phase
     const float2* tw;
     Stages st;
 };

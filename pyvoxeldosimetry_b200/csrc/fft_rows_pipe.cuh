@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NWARPS = NT / 32;
     const float* __restrict__ in0 = g.in[0];
-    const float w0 = g.w[0];
+    const float w0 = 0.5f * g.w[0];  // the 1/2 of the Hermitian split, applied once at the input
     const int n1 = g.n1, n2b = g.n2 * 4;
     // (x, y) of a tile row from the tile's first row: one division per tile instead of one per row
     auto row_xy = [&](int x0, int y0, int rr, int& x, int& y) {
@@ -65,9 +65,8 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
             ++x;
         }
     };
-    auto issue = [&](int t) {  // one warp per row: the row address is warp-uniform, lanes walk the 16-byte chunks
+    auto issue = [&](int t, int x0, int y0) {  // one warp per row: the row address is warp-uniform, lanes walk the 16-byte chunks
         const int row0 = t * 32;
-        const int x0 = row0 / n1, y0 = row0 - x0 * n1;
         for (int rr = warp; rr < 32; rr += NWARPS) {
             const bool valid = row0 + rr < (int)nrows;
             long long off = 0;
@@ -86,7 +85,19 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
         }
     };
     int t = blockIdx.x;
-    if (t < ntiles) issue(t);
+    // (x, y) of the first row of the current tile and of the next one, advanced without divisions
+    const int step = 32 * (int)gridDim.x;
+    const int sx = step / n1, sy = step - sx * n1;
+    int cx = (32 * t) / n1, cy = 32 * t - cx * n1;
+    auto advance = [&](int& x, int& y) {
+        x += sx;
+        y += sy;
+        if (y >= n1) {
+            y -= n1;
+            ++x;
+        }
+    };
+    if (t < ntiles) issue(t, cx, cy);
     cp_async_commit();
     const int wl = threadIdx.x % W;
     // line wl packs staged rows wl (re) and wl + 16 (im): row starts are then 20 (mod 32) banks apart for
@@ -96,13 +107,15 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
     for (; t < ntiles; t += gridDim.x) {
         cp_async_wait<0>();
         __syncthreads();  // staged rows of tile t visible; previous tile's split phase finished with `tile`
-        auto raw_in = [&](int, int, int idx, int) -> float2 { return make_float2(w0 * rawA[idx], w0 * rawB[idx]); };
+        auto raw_in = [&](int, int, int idx, int) -> float2 { return make_float2(w0 * rawA[idx], w0 * rawB[idx]); };  // w0 = w/2
         auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
         auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
         fast_stage<N, W, NT, R1, 1, -1, false>(raw_in, sm_out, tws);
         __syncthreads();  // staging buffer consumed -> refill it with the next tile while the rest runs
         const int tn = t + gridDim.x;
-        if (tn < ntiles) issue(tn);
+        int nx = cx, ny = cy;
+        advance(nx, ny);
+        if (tn < ntiles) issue(tn, nx, ny);
         cp_async_commit();
         if constexpr (R3 > 1) {
             fast_stage<N, W, NT, R2, R1, -1, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1);
@@ -112,17 +125,22 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
             fast_stage<N, W, NT, R2, R1, -1, true>(sm_in, sm_out, tws);
         }
         __syncthreads();
-        // Hermitian split: A[k] = (Z[k] + conj(Z[N-k]))/2, B[k] = (Z[k] - conj(Z[N-k]))/(2i)
+        // Hermitian split: A[k] = (Z[k] + conj(Z[N-k]))/2, B[k] = (Z[k] - conj(Z[N-k]))/(2i).  One warp per LINE: the
+        // pair (Z[k], Z[N-k]) is read once and yields both rows; the factor 1/2 is already in the input weight.
         const int row0 = t * 32;
-        const int x0 = row0 / n1, y0 = row0 - x0 * n1;
+        const int x0 = cx, y0 = cy;
         const int Nh = g.Nh;
-        for (int rr = warp; rr < 32; rr += NWARPS) {
-            if (row0 + rr >= (int)nrows) continue;
+        for (int line = warp; line < W; line += NWARPS) {
+            const bool va = row0 + line < (int)nrows, vb = row0 + line + W < (int)nrows;
+            if (!va) continue;  // rows are consecutive: b valid implies a valid
             int x, y;
-            row_xy(x0, y0, rr, x, y);
-            float2* __restrict__ dst = g.out + x * g.out_s0 + y * g.out_s1;
-            const int line = rr & (W - 1);
-            const bool odd = rr >= W;
+            row_xy(x0, y0, line, x, y);
+            float2* __restrict__ dsta = g.out + x * g.out_s0 + y * g.out_s1;
+            float2* __restrict__ dstb = dsta;
+            if (vb) {
+                row_xy(x0, y0, line + W, x, y);
+                dstb = g.out + x * g.out_s0 + y * g.out_s1;
+            }
             constexpr int KIT = (N / 2 + 1 + 31) / 32;
             PVD_UNROLL
             for (int i = 0; i < KIT; ++i) {
@@ -130,11 +148,13 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
                 if (k < Nh) {
                     const float2 zk = tile[k * LS + line];
                     const float2 zm = tile[((k == 0) ? 0 : N - k) * LS + line];
-                    dst[k] = odd ? make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x))
-                                 : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                    dsta[k] = make_float2(zk.x + zm.x, zk.y - zm.y);
+                    if (vb) dstb[k] = make_float2(zk.y + zm.y, zm.x - zk.x);
                 }
             }
         }
+        cx = nx;
+        cy = ny;
     }
     cp_async_wait<0>();
 }
@@ -204,9 +224,8 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
             ++x;
         }
     };
-    auto issue_spec = [&](int t) {
+    auto issue_spec = [&](int t, int x0, int y0) {
         const int row0 = t * 32;
-        const int x0 = row0 / O1, y0 = row0 - x0 * O1;
         for (int rr = warp; rr < 32; rr += NWARPS) {
             const bool valid = row0 + rr < (int)nrows;
             long long off = 0;
@@ -225,7 +244,19 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
         }
     };
     int t = blockIdx.x;
-    if (t < ntiles) issue_spec(t);
+    // (x, y) of the first row of the current tile and of the next one, advanced without divisions
+    const int step = 32 * (int)gridDim.x;
+    const int sx = step / O1, sy = step - sx * O1;
+    int cx = (32 * t) / O1, cy = 32 * t - cx * O1;
+    auto advance = [&](int& x, int& y) {
+        x += sx;
+        y += sy;
+        if (y >= O1) {
+            y -= O1;
+            ++x;
+        }
+    };
+    if (t < ntiles) issue_spec(t, cx, cy);
     cp_async_commit();
     const float sr = g.scale * (has_den ? g.rho_ref : 1.f), rho_min = g.rho_min, rho_cut = g.rho_cut;
     const int wl = threadIdx.x % W;
@@ -255,13 +286,15 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
         }
         __syncthreads();  // staging buffer consumed: the next tile's spectrum rows stream in during the FFT and the stores
         const int tn = t + gridDim.x;
-        if (tn < ntiles) issue_spec(tn);
+        int nx = cx, ny = cy;
+        advance(nx, ny);
+        if (tn < ntiles) issue_spec(tn, nx, ny);
         cp_async_commit();
         if (has_den && g.den_pf) {
             // the density rows of THIS tile are needed after the inverse transform (~10 us from now): pull their
             // 128-byte lines into L2 now so that the store phase does not wait a full DRAM round trip per row
             const int r0 = t * 32;
-            const int px0 = r0 / O1, py0 = r0 - px0 * O1;
+            const int px0 = cx, py0 = cy;
             const int lines_per_row = (O2 * 4 + 127) / 128;
             for (int i = threadIdx.x; i < 32 * lines_per_row; i += NT) {
                 const int rr = i / lines_per_row, ln = i - rr * lines_per_row;
@@ -283,7 +316,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
         fast_fft<N, W, LS, NT, +1, R1, R2, R3, true, true>(sm_in, row_out, tile, tws);
         __syncthreads();  // all rows complete
         const int row0 = t * 32;
-        const int x0 = row0 / O1, y0 = row0 - x0 * O1;
+        const int x0 = cx, y0 = cy;
         for (int rr = warp; rr < 32; rr += NWARPS) {
             if (row0 + rr >= (int)nrows) continue;
             int x, y;
@@ -299,6 +332,10 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
                     const int z = 4 * (lane + 32 * i);
                     rho[i] = (z < O2) ? ldg128_ro(dg + z) : make_float4(1.f, 1.f, 1.f, 1.f);
                 }
+                // Keep the QIT loads of the row in flight TOGETHER: ptxas otherwise sinks each load to just before its own
+                // use in the register-heavy instantiations (one load in flight instead of four: P5<432> 0.42 -> 0.53 ms).
+                // A warp barrier is a scheduling fence for memory operations; the lanes of the warp are convergent here.
+                __syncwarp();
                 PVD_UNROLL
                 for (int i = 0; i < QIT; ++i) {
                     const int z = 4 * (lane + 32 * i);
@@ -332,6 +369,8 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
                 }
             }
         }
+        cx = nx;
+        cy = ny;
     }
     cp_async_wait<0>();
 }

@@ -89,6 +89,16 @@ static inline float __shfl_sync(unsigned, float v, int src) {
     return v;
 }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline unsigned __float_as_uint(float f) {
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+static inline float __uint_as_float(unsigned u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }

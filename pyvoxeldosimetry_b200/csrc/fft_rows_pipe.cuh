@@ -77,10 +77,14 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
             }
             const float* src = in0 + off;
             float* dstp = raw + rr * LSF;
+            const int nfull = valid ? (n2b >> 4) : 0;  // chunks entirely inside the row; at most one partial chunk follows
+            const int rem = valid ? (n2b & 15) : 0;
             PVD_UNROLL
             for (int i = 0; i < (CHR + 31) / 32; ++i) {
                 const int ch = lane + 32 * i;
-                if (ch < CHR) cp_async16_partial(dstp + ch * 4, src + ch * 4, valid ? n2b - ch * 16 : 0);
+                if (ch < nfull) cp_async16_full(dstp + ch * 4, src + ch * 4);
+                else if (ch == nfull && rem) cp_async16_partial(dstp + ch * 4, src + ch * 4, rem);
+                else if (ch < CHR) st_zero16(dstp + ch * 4);
             }
         }
     };
@@ -239,7 +243,10 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
             PVD_UNROLL
             for (int i = 0; i < (CHC + 31) / 32; ++i) {
                 const int ch = lane + 32 * i;
-                if (ch < CHC) cp_async16(dstp + ch * 2, src + ch * 2, valid);
+                if (ch < CHC) {
+                    if (valid) cp_async16_full(dstp + ch * 2, src + ch * 2);
+                    else st_zero16(dstp + ch * 2);
+                }
             }
         }
     };

@@ -672,7 +672,8 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
         return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (rows)");
     if (p->fastRows && p->fastRows->fwdPipe && p->fastRows->smemPipe <= kMaxSmem) {
         const FastRows* f = p->fastRows;
-        if (PVD_SET_SMEM(f->fwdPipe, kMaxSmem) != 0 || PVD_SET_SMEM(f->invPipe, kMaxSmem) != 0)
+        // exact sizes: the kernels also hold a little static shared memory, so "the maximum" would overshoot
+        if (PVD_SET_SMEM(f->fwdPipe, f->smemPipe) != 0 || PVD_SET_SMEM(f->invPipe, f->smemPipe) != 0)
             return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (rows pipe)");
         int dev = 0, sms = 0, per = 0;
         cudaGetDevice(&dev);

@@ -106,8 +106,24 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         return self._aniso_kernels[sp], ("sp", sp)
 
     # ------------------------------------------------------------------ core
+    def _density_from_ct(self, ct_hu, shape) -> torch.Tensor:
+        """CT volume in Hounsfield units (int16 as scanners store it, or float) -> device density map through the
+        piecewise-linear HU table (`hu_knots` config, default tissue.HU_KNOTS); the conversion runs on the device,
+        so an int16 CT crosses the PCIe link at 2 bytes per voxel."""
+        from ..tissue.density import HU_KNOTS
+
+        if isinstance(ct_hu, torch.Tensor):
+            t = ct_hu if ct_hu.dtype in (torch.int16, torch.float32) else ct_hu.to(torch.float32)
+        else:
+            a = np.ascontiguousarray(ct_hu)
+            t = torch.from_numpy(a if a.dtype in (np.int16, np.float32) else a.astype(np.float32))
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("ct_hu must have the shape of the activity map")
+        t = t.to(self.device, non_blocking=True).contiguous()
+        return engine.hu_to_density(t, self.config.get("hu_knots", HU_KNOTS))
+
     def _convolve(self, maps: Sequence, weights: Optional[Sequence[float]], voxel_size, tissue_densities=None,
-                  out: Optional[np.ndarray] = None):
+                  out: Optional[np.ndarray] = None, ct_hu=None):
         if len(maps) == 0:
             raise ValueError("No activity maps provided")
         shape = tuple(maps[0].shape)
@@ -119,10 +135,14 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         plan = self._plans.get(shape, tuple(kdev.shape), self.boundary, self.device, tag, lambda: kdev, self.algo)
         acts = [engine.to_device_f32(m, self.device) for m in maps]
         den = None
+        if tissue_densities is not None and ct_hu is not None:
+            raise ValueError("give tissue_densities or ct_hu, not both")
         if tissue_densities is not None:
             den = engine.to_device_f32(tissue_densities, self.device)
             if tuple(den.shape) != plan.out_shape:
                 raise ValueError("tissue_densities must have the shape of the activity map")
+        elif ct_hu is not None:
+            den = self._density_from_ct(ct_hu, plan.out_shape)
         cfg = self.config
         dose = plan.execute(acts, weights, den, float(cfg.get("rho_ref", 1.0)), float(cfg.get("rho_min", 0.1)),
                             float(cfg.get("rho_cut", 0.0)), float(cfg.get("scale", 1.0)))
@@ -139,27 +159,43 @@ class KernelConvolutionCalculator(DosimetryCalculator):
 
     # ------------------------------------------------------------------ reference API
     def calculate_dose_rate(self, activity_map, voxel_size: Tuple[float, float, float] = None,
-                            tissue_densities=None, out=None):
-        """A1.  Host ndarray in -> host ndarray out; CUDA tensor in -> CUDA tensor out (no copies)."""
-        dose = self._convolve([activity_map], None, voxel_size, tissue_densities)
+                            tissue_densities=None, out=None, ct_hu=None):
+        """A1.  Host ndarray in -> host ndarray out; CUDA tensor in -> CUDA tensor out (no copies).
+        Density correction (A9): `tissue_densities` (g/cm3) or `ct_hu` (the CT in Hounsfield units, int16 or float)."""
+        dose = self._convolve([activity_map], None, voxel_size, tissue_densities, ct_hu=ct_hu)
         if isinstance(activity_map, torch.Tensor) and activity_map.is_cuda:
             return dose
         return self._to_host(dose, out)
 
     def calculate_dose_rate_batch(self, activity_maps: Sequence, voxel_size=None, tissue_densities=None,
-                                  outs: Optional[Sequence] = None) -> list:
+                                  outs: Optional[Sequence] = None, ct_hu=None) -> list:
         """A1 for a batch of independent host volumes (one per patient / time point), software pipelined:
         the H2D copy of volume i+1, the convolution of volume i and the D2H copy of volume i-1 run on three
         CUDA streams with double-buffered device tensors, so the PCIe link (the end-to-end bottleneck: the
         convolution itself is ~1 ms) works in both directions at once.  `tissue_densities` is None, one
         volume shared by all, or one per activity map.  `outs`: optional host tensors/arrays to fill (pinned
-        host tensors avoid a staging copy; they may repeat, e.g. two alternating buffers)."""
+        host tensors avoid a staging copy; they may repeat, e.g. two alternating buffers).  `ct_hu`: instead of
+        densities, one int16 CT volume (Hounsfield units) per activity map (or one shared); it is copied as int16
+        (2 bytes per voxel over the link) and turned into density on the device."""
         n = len(activity_maps)
+        if ct_hu is not None:
+            if tissue_densities is not None:
+                raise ValueError("give tissue_densities or ct_hu, not both")
+            from ..tissue.density import HU_KNOTS
+
+            knots = self.config.get("hu_knots", HU_KNOTS)
+            if not isinstance(ct_hu, (list, tuple)):
+                tissue_densities, ct_hu = self._density_from_ct(ct_hu, tuple(activity_maps[0].shape)) if n else None, None
         if n == 0:
             return []
         shape = tuple(activity_maps[0].shape)
         if any(tuple(a.shape) != shape for a in activity_maps):
             raise ValueError("All activity maps must have the same dimensions")
+        per_vol_ct = ct_hu is not None
+        if per_vol_ct:
+            if len(ct_hu) != n:
+                raise ValueError("need one CT volume per activity map")
+            tissue_densities = ct_hu
         per_vol_den = isinstance(tissue_densities, (list, tuple))
         if per_vol_den and len(tissue_densities) != n:
             raise ValueError("need one density volume per activity map")
@@ -173,6 +209,10 @@ class KernelConvolutionCalculator(DosimetryCalculator):
             t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
             return t if t.dtype == torch.float32 else t.to(torch.float32)
 
+        def host_i16(x):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            return t if t.dtype == torch.int16 else t.to(torch.int16)
+
         s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         start = torch.cuda.Event()
         start.record(torch.cuda.current_stream(dev))
@@ -184,6 +224,8 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         if tissue_densities is not None:
             if per_vol_den:
                 d_den = [torch.empty(plan.out_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+                if per_vol_ct:
+                    d_hu = [torch.empty(plan.out_shape, dtype=torch.int16, device=dev) for _ in range(2)]
             else:
                 shared = engine.to_device_f32(tissue_densities, dev)
                 start2 = torch.cuda.Event()
@@ -199,7 +241,12 @@ class KernelConvolutionCalculator(DosimetryCalculator):
                 if i >= 2:
                     s_in.wait_event(ev_cmp[i - 2])  # device input slot free again
                 d_act[slot].copy_(host_f32(activity_maps[i]), non_blocking=True)
-                if d_den is not None:
+                if d_den is not None and per_vol_ct:
+                    h = host_i16(tissue_densities[i])
+                    if tuple(h.shape) != plan.out_shape:
+                        raise ValueError("ct_hu must have the shape of the activity map")
+                    d_hu[slot].copy_(h, non_blocking=True)
+                elif d_den is not None:
                     d_den[slot].copy_(host_f32(tissue_densities[i]), non_blocking=True)
                 ev_in[i].record(s_in)
             with torch.cuda.stream(s_cmp):
@@ -207,6 +254,8 @@ class KernelConvolutionCalculator(DosimetryCalculator):
                 if i >= 2:
                     s_cmp.wait_event(ev_out[i - 2])  # device output slot drained
                 den = None if tissue_densities is None else (d_den[slot] if d_den is not None else shared)
+                if per_vol_ct:  # HU -> density on the device, in the compute stream (d_den[slot] is free: see ev_out wait)
+                    self._lib_hu_to_density(d_hu[slot], knots, d_den[slot])
                 plan.execute([d_act[slot]], None, den, rr, rm, rc, sc, out=d_out[slot])
                 ev_cmp[i].record(s_cmp)
             with torch.cuda.stream(s_out):
@@ -222,13 +271,18 @@ class KernelConvolutionCalculator(DosimetryCalculator):
             s.synchronize()
         return [r.numpy() for r in results]
 
+    def _lib_hu_to_density(self, hu: torch.Tensor, knots, rho: torch.Tensor) -> None:
+        with torch.cuda.device(self.device):
+            engine.get_lib().hu_to_density(hu.data_ptr(), hu.dtype == torch.int16, knots, rho.data_ptr(), hu.numel(),
+                                           torch.cuda.current_stream(self.device).cuda_stream)
+
     def calculate_absorbed_dose(self, activity_maps, time_points: List[float], voxel_size=None,
-                                tissue_densities=None, out=None):
+                                tissue_densities=None, out=None, ct_hu=None):
         """A2.  time_points in hours; dose = sum_i w_i * conv(a_i, k), w = trapezoid weights * 3600."""
         if len(activity_maps) != len(time_points):
             raise ValueError("Number of activity maps must match number of time points")
         w = trapezoid_weights(time_points, HOURS_TO_SECONDS)
-        dose = self._convolve(list(activity_maps), w, voxel_size, tissue_densities)
+        dose = self._convolve(list(activity_maps), w, voxel_size, tissue_densities, ct_hu=ct_hu)
         if isinstance(activity_maps[0], torch.Tensor) and activity_maps[0].is_cuda:
             return dose
         return self._to_host(dose, out)

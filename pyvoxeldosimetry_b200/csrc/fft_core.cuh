@@ -87,7 +87,13 @@ __host__ __device__ __forceinline__ float2 mulw(float2 a) {
     } else {
         constexpr float c = TwC<n, DEN>::c;
         constexpr float s = DIR * TwC<n, DEN>::s;
+#if defined(__CUDA_ARCH__) && !defined(PVD_EMULATE) && PVD_F32X2 > 1
+        // a*c + (-a.y*s, a.x*s): two scalar products feed one packed fma (3 instructions instead of 4); the rounding
+        // differs from the scalar form only in which product is fused
+        return __ffma2_rn(a, make_float2(c, c), make_float2(-a.y * s, a.x * s));
+#else
         return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+#endif
     }
 }
 
@@ -128,10 +134,15 @@ struct Dft {
                     constexpr int j = decltype(jc)::value;
                     constexpr float c = TwC<(j * k) % R, R>::c;
                     constexpr float s = TwC<(j * k) % R, R>::s;
+#if defined(__CUDA_ARCH__) && !defined(PVD_EMULATE) && PVD_F32X2
+                    A = __ffma2_rn(sp[j], make_float2(c, c), A);
+                    B = __ffma2_rn(dm[j], make_float2(s, s), B);
+#else
                     A.x += sp[j].x * c;
                     A.y += sp[j].y * c;
                     B.x += dm[j].x * s;
                     B.y += dm[j].y * s;
+#endif
                 });
                 // X_k = A + DIR*i*B ; X_{R-k} = A - DIR*i*B
                 a[k] = make_float2(A.x - DIR * B.y, A.y + DIR * B.x);

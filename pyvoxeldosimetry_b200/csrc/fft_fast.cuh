@@ -199,8 +199,10 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
     float2* tile = smem;
     float2* tws = smem + N * W;
     float2* twr = SYM ? tws : tws + Fwd::TOTAL;
+    grid_dep_launch();
     Fwd::build(tws, g.tw);
     if constexpr (MODE == COL_CONV && !SYM) Rev::build(twr, g.tw);
+    grid_dep_wait();
     const int z0 = blockIdx.x * W;
     const long long base = (long long)(g.outer0 + (int)blockIdx.y) * g.os + z0;
     const int zlim = g.nzf - z0;
@@ -233,12 +235,12 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
         // L2 prefetch (no registers held): the spectrum lines this CTA multiplies by after its forward transform, and
         // the input lines of the tile that the CTA scheduled into this slot next will most likely get (blocks are
         // dispatched in linear order, pf_dist = CTAs resident on the whole GPU) - their first-stage loads then hit L2.
-        if (g.pf_dist > 0) {
+        if (g.pf_dist != 0) {  // pf_dist < 0: spectrum lines only
             const float2* sp0 = g.spec + base;
             for (int r = threadIdx.x; r < g.M; r += NT) prefetch_l2(sp0 + (size_t)r * es);
             const long long nxt = (long long)blockIdx.y * gridDim.x + blockIdx.x + g.pf_dist;
             const long long ny = nxt / gridDim.x, nx = nxt - ny * gridDim.x;
-            if (ny < gridDim.y) {
+            if (g.pf_dist > 0 && ny < gridDim.y) {
                 const float2* in0 = g.in + (long long)(g.outer0 + (int)ny) * g.os + nx * W;
                 for (int r = threadIdx.x; r < n_in; r += NT) prefetch_l2(in0 + (size_t)r * es);
             }

@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const ColPipeArgs p
     PVD_DYN_SMEM(float2, smem);
     float2* tws = smem + 2 * N * W;
     float2* twr = SYM ? tws : tws + Fwd::TOTAL;
+    grid_dep_launch();
     Fwd::build(tws, g.tw);
     if constexpr (MODE == COL_CONV && !SYM) Rev::build(twr, g.tw);
+    grid_dep_wait();
     const unsigned es = (unsigned)g.es;
     const unsigned esb = es * (unsigned)sizeof(float2);
     const int n_in = g.n_in;

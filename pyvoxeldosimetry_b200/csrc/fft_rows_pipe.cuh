@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
     float2* tile = smem;
     float* raw = reinterpret_cast<float*>(smem + N * LS);
     float2* tws = reinterpret_cast<float2*>(raw + 32 * LSF);
-    Sched<N, R1, R2, R3>::build(tws, g.tw);
+    grid_dep_launch();
+    Sched<N, R1, R2, R3>::build(tws, g.tw);  // tables come from the plan's twiddle buffer (complete since plan set-up)
+    grid_dep_wait();                         // predecessor grid done: its output / our output buffer may be touched now
     const long long nrows = (long long)g.n0 * g.n1;
     const int ntiles = (int)((nrows + 31) / 32);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -211,7 +213,9 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
     float* rowbuf = reinterpret_cast<float*>(smem);
     float2* rawc = smem + N * LS;  // staged complex rows
     float2* tws = rawc + 32 * LSC;
+    grid_dep_launch();
     Sched<N, R1, R2, R3>::build(tws, g.tw);
+    grid_dep_wait();
     const long long nrows = (long long)g.O0 * g.O1;
     const int ntiles = (int)((nrows + 31) / 32);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

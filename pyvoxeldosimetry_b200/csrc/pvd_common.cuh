@@ -166,6 +166,9 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
 }
 }  // namespace pvd_emu
 #define PVD_LAUNCH(kernel, grid, block, smem, stream, ...) pvd_emu::launch(kernel, grid, block, smem, __VA_ARGS__)
+#define PVD_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, arg) pvd_emu::launch(kernel, grid, block, smem, arg)
+static inline void grid_dep_wait() {}
+static inline void grid_dep_launch() {}
 #define PVD_SET_SMEM(kernel, bytes) (0)
 static constexpr int PVD_BLOCK = 32;  // small blocks keep the emulator fast; kernels are block-size agnostic
 
@@ -177,6 +180,29 @@ static constexpr int PVD_BLOCK = 32;  // small blocks keep the emulator fast; ke
     extern __shared__ __align__(16) unsigned char pvd_dyn_smem_raw[]; \
     T* name = reinterpret_cast<T*>(pvd_dyn_smem_raw)
 #define PVD_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// Programmatic dependent launch (sm_90+): the kernel may be scheduled while its predecessor in the stream drains, so
+// that launch latency, CTA start-up and the twiddle-table prologue overlap the predecessor's tail.  Every kernel
+// launched this way calls grid_dep_wait() before it touches data the predecessor may have written (the wait returns
+// once the predecessor grid has completed and its writes are visible) and grid_dep_launch() to let ITS successor in.
+template <class Arg>
+static inline cudaError_t pvd_launch_pdl(bool pdl, void (*kernel)(const Arg), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t stream, const Arg& arg) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+#define PVD_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, arg) pvd_launch_pdl(pdl, kernel, grid, block, smem, stream, arg)
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #define PVD_SET_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 static constexpr int PVD_BLOCK = 256;
 #endif
@@ -191,8 +217,26 @@ struct Stages {
     int radix[kMaxStages];
 };
 
-__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex add / subtract.  On sm_100a a float2 add is ONE packed instruction (add.f32x2 -> FADD2; the subtraction is
+// fma.f32x2 with the constant pair (-1, -1), exactly rounded like a - b): the butterflies are mostly complex
+// adds, so this removes a third of the floating-point issue slots.  Results are bit-identical to the scalar form.
+#ifndef PVD_F32X2
+#define PVD_F32X2 1
+#endif
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && !defined(PVD_EMULATE) && PVD_F32X2
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && !defined(PVD_EMULATE) && PVD_F32X2
+    return __ffma2_rn(b, make_float2(-1.f, -1.f), a);
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

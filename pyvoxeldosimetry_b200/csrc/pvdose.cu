@@ -247,6 +247,7 @@ struct pvd_plan {
     const FastCols* fastCols[2] = {nullptr, nullptr};  // size-specialised kernels, when the length is on the menu
     const FastRows* fastRows = nullptr;
     bool usePipe = true;
+    bool pdl = true;  // programmatic dependent launch of the specialised kernels (PVD_PDL=0 turns it off)
     int pipeGrid[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // persistent grid size per axis / mode
     int rowPipeGrid[2] = {0, 0};                        // persistent grid size of the row passes (fwd, inv)
     int fnGrid[2] = {0, 0};                             // CTAs of the one-tile-per-CTA CONV kernel resident on the GPU
@@ -313,7 +314,7 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
         ((uintptr_t)in[0] & 15) == 0) {
         const FastRows* f = p->fastRows;
         const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[0]);
-        PVD_LAUNCH(f->fwdPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
+        PVD_LAUNCH_PDL(p->pdl, f->fwdPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
         PVD_CUDA_CHECK("rows_fwd_pipe_kernel");
         return PVD_OK;
     }
@@ -362,7 +363,7 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
         if (pa.ntz == 1) pa.ntz_magic = 0xFFFFFFFFu;
         const size_t smem = ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2);
         const int grid = std::min(pa.ntiles, p->pipeGrid[axis][mode]);
-        PVD_LAUNCH(f->pipe[mode], dim3((unsigned)grid), dim3(f->pipeNT[mode]), smem, stream, pa);
+        PVD_LAUNCH_PDL(p->pdl, f->pipe[mode], dim3((unsigned)grid), dim3(f->pipeNT[mode]), smem, stream, pa);
         PVD_CUDA_CHECK("cols_pipe_kernel");
         return PVD_OK;
     }
@@ -375,7 +376,7 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
             const char* e = getenv("PVD_PF_DIST");
             a.pf_dist = e ? atoi(e) : 0;
         }
-        PVD_LAUNCH(f->fn[mode], dim3((unsigned)((p->Nh + 15) / 16), (unsigned)nouter), dim3(f->fnNT[mode]), smem, stream, a);
+        PVD_LAUNCH_PDL(p->pdl, f->fn[mode], dim3((unsigned)((p->Nh + 15) / 16), (unsigned)nouter), dim3(f->fnNT[mode]), smem, stream, a);
         PVD_CUDA_CHECK("cols_fast_kernel");
         return PVD_OK;
     }
@@ -791,7 +792,7 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     if (p->fastRows && p->usePipe && p->rowPipeGrid[1] > 0 && nrows < 2000000000LL) {
         const FastRows* f = p->fastRows;
         const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[1]);
-        PVD_LAUNCH(f->invPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
+        PVD_LAUNCH_PDL(p->pdl, f->invPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
         PVD_CUDA_CHECK("rows_inv_pipe_kernel");
         p->mark_end(stream);
         return PVD_OK;

@@ -230,3 +230,32 @@ def test_pipelined_batch_api_matches_single_calls():
     r = calc.calculate_dose_rate_batch(vols[:3], (1.0, 1.0, 1.0), None, outs)
     assert orc.rel_err_of_peak(r[2], orc.conv_same(f64(vols[2]), f64(calc.kernel))) <= TOL
     assert calc.calculate_dose_rate_batch([], (1.0, 1.0, 1.0)) == []
+
+
+def test_ct_hu_input_matches_oracle_and_density_route():
+    """Density correction from the CT itself (int16 Hounsfield units, converted on the device) equals the route
+    through host-side densities and the float64 oracle (conv + HU table + density correction)."""
+    from pyvoxeldosimetry_b200 import KernelConvolutionCalculator
+
+    rng = np.random.default_rng(17)
+    shape = (40, 48, 56)
+    calc = KernelConvolutionCalculator("Y90", "water", 1.0, config={"kernel_grid": (9, 9, 9), "boundary": "same"})
+    vols = [rng.uniform(0, 1e3, shape).astype(np.float32) for _ in range(4)]
+    cts = [rng.integers(-1000, 1500, size=shape).astype(np.int16) for _ in range(4)]
+    k64 = f64(calc.kernel)
+    got = calc.calculate_dose_rate(vols[0], (1.0, 1.0, 1.0), ct_hu=cts[0])
+    ref = orc.density_correct(orc.conv_same(f64(vols[0]), k64), orc.hu_to_density(cts[0]))
+    assert orc.rel_err_of_peak(got, ref) <= TOL
+    batch = calc.calculate_dose_rate_batch(vols, (1.0, 1.0, 1.0), ct_hu=cts)
+    for v, c, b in zip(vols, cts, batch):
+        assert np.array_equal(b, calc.calculate_dose_rate(v, (1.0, 1.0, 1.0), ct_hu=c))
+    shared = calc.calculate_dose_rate_batch(vols[:2], (1.0, 1.0, 1.0), ct_hu=cts[1])
+    assert np.array_equal(shared[0], calc.calculate_dose_rate(vols[0], (1.0, 1.0, 1.0), ct_hu=cts[1]))
+    dose = calc.calculate_absorbed_dose(vols[:3], [1.0, 5.0, 20.0], (1.0, 1.0, 1.0), ct_hu=cts[2].astype(np.float32))
+    w = [2.0 * 3600, (2.0 + 7.5) * 3600, 7.5 * 3600]
+    acc = sum(wi * f64(v) for wi, v in zip(w, vols[:3]))
+    assert orc.rel_err_of_peak(dose, orc.density_correct(orc.conv_same(acc, k64), orc.hu_to_density(cts[2]))) <= TOL
+    with pytest.raises(ValueError):
+        calc.calculate_dose_rate(vols[0], (1.0, 1.0, 1.0), tissue_densities=np.ones(shape, np.float32), ct_hu=cts[0])
+    with pytest.raises(ValueError):
+        calc.calculate_dose_rate(vols[0], (1.0, 1.0, 1.0), ct_hu=cts[0][:-1])

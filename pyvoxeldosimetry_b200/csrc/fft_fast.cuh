@@ -199,38 +199,53 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
     float2* tile = smem;
     float2* tws = smem + N * W;
     float2* twr = SYM ? tws : tws + Fwd::TOTAL;
+    // The one-tile-per-CTA form is launched normally (fully serialised behind its predecessor): as a programmatic
+    // dependent every one of its thousands of CTAs paid the grid-dependency wait (C3: +70 us per volume, measured).
+    // It still lets ITS successor start early.
     grid_dep_launch();
     Fwd::build(tws, g.tw);
     if constexpr (MODE == COL_CONV && !SYM) Rev::build(twr, g.tw);
-    grid_dep_wait();
-    const int z0 = blockIdx.x * W;
-    const long long base = (long long)(g.outer0 + (int)blockIdx.y) * g.os + z0;
-    const int zlim = g.nzf - z0;
+    // Tile walk.  2-D grid: one tile per CTA (zt = blockIdx.x, outer = blockIdx.y).  loop_ntiles > 0: a 1-D grid of
+    // resident CTAs strides over the linear tile list - the table build and the CTA start-up are paid once per CTA
+    // instead of once per tile.  The first radix stage issues its global loads and THEN meets the block barrier
+    // (IN_SMEM = true below): that barrier publishes the twiddle tables on the first tile and frees the exchange
+    // tile on the following ones, and it does not wait for the loads themselves.
+    const bool looped = g.loop_ntiles > 0;
+    if (looped) grid_dep_wait();  // the persistent form is launched as a programmatic dependent: one wait per CTA
+    const int tend = looped ? g.loop_ntiles : 1, tstep = looped ? (int)gridDim.x : 1;
     const unsigned es = (unsigned)g.es;
     const unsigned esb = es * (unsigned)sizeof(float2);  // stride between transform indices in bytes
     const int wl = threadIdx.x % W, b0 = threadIdx.x / W;
-    const bool wok = wl < zlim;
-    const float2* src = opaque(g.in + base + (size_t)b0 * es + wl);
-    float2* dst = opaque(g.out + base + (size_t)b0 * es + wl);
     const int n_in = g.n_in;
     const unsigned cnt = (unsigned)g.out_n;
     const int blo = b0 - g.out_lo;
     constexpr int NB1 = N / R1;
+    for (int t = looped ? (int)blockIdx.x : 0; t < tend; t += tstep) {
+    int zt = blockIdx.x, outer = blockIdx.y;
+    if (looped) {
+        outer = t / g.loop_ntz;
+        zt = t - outer * g.loop_ntz;
+    }
+    const int z0 = zt * W;
+    const long long base = (long long)(g.outer0 + outer) * g.os + z0;
+    const int zlim = g.nzf - z0;
+    const bool wok = wl < zlim;
+    const float2* src = opaque(g.in + base + (size_t)b0 * es + wl);
+    float2* dst = opaque(g.out + base + (size_t)b0 * es + wl);
     auto gin = [&](int u, int j, int r, int) -> float2 {
         return (wok && r < n_in) ? ldg64(eptr(src, esb, u * TPC + NB1 * j)) : make_float2(0.f, 0.f);
     };
     auto gout = [&](int u, int k, int, int, float2 v) {
         if (wok && (unsigned)(blo + u * TPC + LS_::STEP * k) < cnt) stg64(eptr(dst, esb, u * TPC + LS_::STEP * k), v);
     };
-    __syncthreads();  // twiddle tables visible
     if constexpr (MODE == COL_FWD) {
-        fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, gout, tile, tws);
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, gout, tile, tws);
     } else if constexpr (MODE == COL_SPEC) {
         const float sc = g.scale;
         auto sout = [&](int u, int k, int r, int w, float2 v) { gout(u, k, r, w, make_float2(v.x * sc, v.y * sc)); };
-        fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, sout, tile, tws);
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, sout, tile, tws);
     } else if constexpr (MODE == COL_INV) {
-        fast_fft<N, W, W, NT, +1, R1, R2, R3, false, false>(gin, gout, tile, tws);
+        fast_fft<N, W, W, NT, +1, R1, R2, R3, true, false>(gin, gout, tile, tws);
     } else {  // COL_CONV: forward -> * spectrum -> inverse, the middle never leaves registers
         // L2 prefetch (no registers held): the spectrum lines this CTA multiplies by after its forward transform, and
         // the input lines of the tile that the CTA scheduled into this slot next will most likely get (blocks are
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
         }
         float2 hold[BPTL][RL];
         auto rout = [&](int u, int k, int, int, float2 v) { hold[u][k] = v; };
-        fast_fft<N, W, W, NT, -1, R1, R2, R3, false, false>(gin, rout, tile, tws);
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, rout, tile, tws);
         const float2* sp = opaque(g.spec + base + (size_t)b0 * es + wl);
         PVD_UNROLL
         for (int u = 0; u < BPTL; ++u) {
@@ -268,6 +283,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
         else
             fast_fft<N, W, W, NT, +1, R2, R1, 1, false, false>(rin, gout_rev, tile, twr);
     }
+    }  // tile walk
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -376,7 +376,19 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
             const char* e = getenv("PVD_PF_DIST");
             a.pf_dist = e ? atoi(e) : 0;
         }
-        PVD_LAUNCH_PDL(p->pdl, f->fn[mode], dim3((unsigned)((p->Nh + 15) / 16), (unsigned)nouter), dim3(f->fnNT[mode]), smem, stream, a);
+        static const int loop_knob = [] { const char* e = getenv("PVD_P3_LOOP"); return e ? atoi(e) : 1; }();
+        if (mode == COL_CONV && loop_knob && p->fnGrid[axis] > 0) {
+            // persistent walk over the tiles with the CTAs that are resident anyway (see cols_fast_kernel)
+            a.loop_ntz = (p->Nh + 15) / 16;
+            a.loop_ntiles = a.loop_ntz * nouter;
+            a.pf_dist = 0;
+            const int grid = std::min(a.loop_ntiles, p->fnGrid[axis]);
+            static const int p3_pdl = [] { const char* e = getenv("PVD_P3_PDL"); return e ? atoi(e) : 0; }();
+            PVD_LAUNCH_PDL(p->pdl && p3_pdl, f->fn[mode], dim3((unsigned)grid), dim3(f->fnNT[mode]), smem, stream, a);
+            PVD_CUDA_CHECK("cols_fast_kernel (looped)");
+            return PVD_OK;
+        }
+        PVD_LAUNCH_PDL(false, f->fn[mode], dim3((unsigned)((p->Nh + 15) / 16), (unsigned)nouter), dim3(f->fnNT[mode]), smem, stream, a);
         PVD_CUDA_CHECK("cols_fast_kernel");
         return PVD_OK;
     }
@@ -439,6 +451,8 @@ int plan_finish(pvd_plan* p) {
     }
     const char* nopipe = getenv("PVD_NO_PIPE");
     p->usePipe = !(nopipe && nopipe[0] == '1');
+    const char* nopdl = getenv("PVD_PDL");
+    p->pdl = !(nopdl && nopdl[0] == '0');
     // ---- direct tiled convolution (TMA halo tiles): 'same'-type geometry, small kernels only
     bool direct_ok = (p->k[2] == 3 || p->k[2] == 5 || p->k[2] == 7) && p->k[0] <= 9 && p->k[1] <= 9 && p->n[2] % 4 == 0;
     for (int i = 0; i < 3; ++i) direct_ok = direct_ok && p->on[i] == p->n[i] && p->olo[i] == p->k[i] / 2;
@@ -647,6 +661,10 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
                    p->m[a]);
         PVD_CUDA_CHECK("twiddle_kernel");
     }
+    // The specialised kernels build their shared-memory twiddle tables from these buffers BEFORE their
+    // grid-dependency wait (programmatic dependent launch), so the tables must be complete before any of them can be
+    // launched: plan set-up is a one-time call, a host-side wait here is the simplest guarantee.
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return fail(PVD_ERR_CUDA, "twiddle tables: stream synchronize failed");
     for (int a = 0; a < 2; ++a)
         if (p->fastCols[a])
             for (int md = 0; md < 4; ++md)

@@ -105,8 +105,13 @@ struct Sched {
 
 // One Stockham DIF stage with radix R and stride S.  in(u, j, idx, w) -> float2, out(u, k, idx, w, v).
 // (u, j)/(u, k) are the register slots (compile-time after unrolling), idx the transform index, w the line.
-template <int N, int W, int NT, int R, int S, int DIR, bool SYNC_AFTER_READ, class In, class Out>
-__device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __restrict__ tws) {
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+// `hook` runs right after the stage's input reads have been ISSUED (and after the optional barrier), before the first
+// use of the loaded values: the place for work that should overlap the load latency (L2 prefetches of later tiles).
+template <int N, int W, int NT, int R, int S, int DIR, bool SYNC_AFTER_READ, class In, class Out, class Hook = NoHook>
+__device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __restrict__ tws, Hook&& hook = Hook()) {
     constexpr int NB = N / R;          // butterflies per line
     constexpr int M = NB / S;
     constexpr int TPC = NT / W;        // butterflies of one line processed concurrently
@@ -126,6 +131,7 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
         }
     }
     if (SYNC_AFTER_READ) __syncthreads();
+    hook();
     PVD_UNROLL
     for (int u = 0; u < BPT; ++u) {
         const int b = b0 + u * TPC;
@@ -159,12 +165,12 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
 // Whole transform.  Stage list (R1, R2, R3) with R3 == 1 meaning two stages.  IN_SMEM / OUT_SMEM say
 // whether `in` / `out` address the exchange tile itself (then reads must complete before writes).
 // `tws` = Sched<N,R1,R2,R3> tables.
-template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out>
-__device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws) {
+template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out, class Hook = NoHook>
+__device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws, Hook&& hook = Hook()) {
     static_assert(R1 * R2 * R3 == N, "radix schedule must multiply to N");
     auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
     auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
-    fast_stage<N, W, NT, R1, 1, DIR, IN_SMEM>(in, sm_out, tws);
+    fast_stage<N, W, NT, R1, 1, DIR, IN_SMEM>(in, sm_out, tws, hook);
     __syncthreads();
     if constexpr (R3 > 1) {
         fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1);
@@ -262,7 +268,20 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
         }
         float2 hold[BPTL][RL];
         auto rout = [&](int u, int k, int, int, float2 v) { hold[u][k] = v; };
-        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, rout, tile, tws);
+        // tile walk: while this tile's first-stage loads are in flight, pull this tile's spectrum lines (bit 1 of
+        // loop_pf) and the input lines of the tile this CTA processes next (bit 0) into L2
+        auto pf_hook = [&]() {
+            if (g.loop_pf & 2) {
+                const float2* sp0 = g.spec + base;
+                for (int r = threadIdx.x; r < g.M; r += NT) prefetch_l2(sp0 + (size_t)r * es);
+            }
+            if ((g.loop_pf & 1) && t + tstep < tend) {
+                const int tn = t + tstep, on = tn / g.loop_ntz, zn = tn - on * g.loop_ntz;
+                const float2* in0 = g.in + (long long)(g.outer0 + on) * g.os + zn * W;
+                for (int r = threadIdx.x; r < n_in; r += NT) prefetch_l2(in0 + (size_t)r * es);
+            }
+        };
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, rout, tile, tws, pf_hook);
         const float2* sp = opaque(g.spec + base + (size_t)b0 * es + wl);
         PVD_UNROLL
         for (int u = 0; u < BPTL; ++u) {

@@ -94,6 +94,7 @@ struct ColArgs {
     int mode;
     float scale;
     int pf_dist;  // one-tile-per-CTA kernels: L2-prefetch the tile of block (linear id + pf_dist); 0 = off
+    int loop_pf;  // tile walk: L2 prefetch mask (1: next tile's input lines, 2: this tile's spectrum lines)
     int loop_ntz, loop_ntiles;  // cols_fast_kernel as a persistent 1-D grid: tiles along the frequency axis / in total (0: 2-D grid, one tile per CTA)
     const float2* tw;
     Stages st;

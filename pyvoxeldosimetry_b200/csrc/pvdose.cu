@@ -382,6 +382,8 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
             a.loop_ntz = (p->Nh + 15) / 16;
             a.loop_ntiles = a.loop_ntz * nouter;
             a.pf_dist = 0;
+            static const int loop_pf = [] { const char* e = getenv("PVD_P3_PF"); return e ? atoi(e) : 0; }();
+            a.loop_pf = loop_pf;
             const int grid = std::min(a.loop_ntiles, p->fnGrid[axis]);
             static const int p3_pdl = [] { const char* e = getenv("PVD_P3_PDL"); return e ? atoi(e) : 0; }();
             PVD_LAUNCH_PDL(p->pdl && p3_pdl, f->fn[mode], dim3((unsigned)grid), dim3(f->fnNT[mode]), smem, stream, a);

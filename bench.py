@@ -290,8 +290,10 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist = None
+    full_affinity = os.sched_getaffinity(0)
+    # host threads (and so the pinned staging buffers of the e2e leg, first touch) on the GPU's own NUMA node
+    sys.stderr.write(bind_to_gpu_numa(local) + "\n")
     if world > 1:
-        sys.stderr.write(bind_to_gpu_numa(local) + "\n")
         import torch.distributed as dist_mod
 
         dist = dist_mod
@@ -438,7 +440,7 @@ def run_ours(args, wl):
         dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
         traffic = None  # dram__bytes_read+write of the whole path from the committed ncu --set full capture (same workload only)
-        tpath = os.path.join(REPO, "profiles", "r01d_dram_traffic_c3.json")
+        tpath = os.path.join(REPO, "profiles", "r01f_dram_traffic_c3.json")
         if args.workload == "c3" and args.boundary == "reference" and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("_whole_path_dram_bytes")
         line = {
@@ -463,6 +465,8 @@ def run_ours(args, wl):
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import dose_oracle as orc
+
+            os.sched_setaffinity(0, full_affinity)  # the CPU leg may use every host core again
 
             k64 = calc.kernel.astype(np.float32).astype(np.float64)
             rate, sample, secs = cpu_reference_time(wl, 20.0, acts_h, rho_h, k64)

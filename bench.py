@@ -28,9 +28,19 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
-# NCCL prints its version banner on STDOUT when NCCL_DEBUG is VERSION/INFO: stdout carries exactly ONE JSON line
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-    os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Native libraries write there too (NCCL prints its version banner on stdout
+# when NCCL_DEBUG is VERSION/INFO in the environment or in a nccl.conf), so file descriptor 1 is pointed at stderr for
+# the whole run and the JSON line goes to the saved, real stdout.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 WORKLOADS = {
     # name: (shape, kernel grid, nuclide, voxel mm, T, density)
@@ -277,7 +287,7 @@ def run_reference(args, wl):
                                 "what": "same mathematics, scipy.fft rfftn/irfftn with workers = all host threads (not the reference's own code path), same sample"}
     except Exception as e:  # pragma: no cover - scipy missing / signature drift: the literal figure stands
         line["cpu_threaded"] = {"unavailable": str(e)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -479,7 +489,7 @@ def run_ours(args, wl):
                                                     "what": "same mathematics via scipy.fft rfftn/irfftn, workers = all host threads, same sample"}
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"]["threaded"] = {"unavailable": str(e)[:200]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -551,7 +561,7 @@ def run_sharded(args, wl, name):
         value = units * 1e3 / ms_step
         alg = 4.0 * (wl["T"] + 1 + (1 if wl["density"] else 0)) * nvox * units
         peak_gbs, peak_src = peaks()
-        print(json.dumps({
+        emit({
             "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox, "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -559,7 +569,7 @@ def run_sharded(args, wl, name):
             "roofline": {"bound": "hbm", "achieved": round(alg / (ms_step * 1e-3) / 1e9, 1), "peak": peak_gbs * world, "unit": "GB/s",
                          "frac": round(alg / (ms_step * 1e-3) / 1e9 / (peak_gbs * world), 4), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
             "gpu_launches": launches * args.steps,
-        }), flush=True)
+        })
     dist.barrier()
     dist.destroy_process_group()
 

@@ -8,6 +8,7 @@
 // tile and consumed after the forward transform.  The point is memory-level parallelism: ncu showed the
 // non-pipelined kernels stalled on long_scoreboard with ~50 % issue activity (profiles/r01_ncu_fast.md).
 #pragma once
+#include "direct_conv.cuh"  // CUtensorMap, mbarrier / TMA helpers
 #include "fft_fast.cuh"
 
 namespace pvd {
@@ -41,14 +42,28 @@ template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 #endif
 
 struct ColPipeArgs {
+    // TMA variant (use_tma): the tile [N indices][16 frequencies] is a 3-D box of this tensor map over the work buffer
+    // - dims (2*Sz floats, rows, outer), box (32 floats, BOXR rows, 1) - so ONE thread issues N/BOXR bulk copies per
+    // tile instead of N*8/NT 16-byte cp.async per thread (ncu: mio_throttle was the top stall of the y passes).
+    alignas(64) CUtensorMap tmap;
     ColArgs c;
     int ntz;     // tiles along the frequency axis
     int ntiles;  // ntz * number of outer indices
     unsigned ntz_magic;  // ceil(2^32 / ntz): t / ntz == __umulhi(t, magic) for t * ntz < 2^32
+    int use_tma;
+    int* error_flag;  // set if a bulk copy never completes (bad descriptor) instead of hanging the GPU
 };
 
+// rows per TMA box: the largest divisor of N that fits the 256-element box limit
+constexpr int tma_box_rows(int n) {
+    int best = 1;
+    for (int d = 1; d <= 256 && d <= n; ++d)
+        if (n % d == 0) best = d;
+    return best;
+}
+
 template <int N, int NT, int MINB, int R1, int R2, int R3, int MODE>
-__global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const ColPipeArgs pa) {
+__global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const __grid_constant__ ColPipeArgs pa) {
     constexpr int W = 16;
     using LS_ = LastStage<N, NT, R1, R2, R3>;
     constexpr int RL = LS_::RL, TPC = LS_::TPC, BPTL = LS_::BPT;
@@ -89,14 +104,48 @@ __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const ColPipeArgs p
         for (int i = 0; i < CHUNKS / NT; ++i)
             cp_async16(dstp + i * ((NT / 8) * W), eptr(src, esb, i * (NT / 8)), crow + i * (NT / 8) < n_in);
     };
+#ifndef PVD_EMULATE
+    constexpr int BOXR = tma_box_rows(N);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 2 * N * W + 4 * N) - 2;  // tail of the table area
+    const bool tma = pa.use_tma && ((unsigned)__cvta_generic_to_shared(smem) & 127u) == 0;
+    unsigned ph0 = 0, ph1 = 0;  // phase parity of the two buffers' mbarriers
+    auto issue_tma = [&](int b, int t) {  // one thread: N/BOXR bulk copies of BOXR rows x 128 bytes
+        int zt;
+        const int outer = (ntz == 1) ? t : (int)__umulhi((unsigned)t, magic);
+        zt = t - outer * ntz;
+        mbar_expect_tx(&bars[b], (unsigned)(N * W * sizeof(float2)));
+        PVD_UNROLL
+        for (int i = 0; i < N / BOXR; ++i)
+            tma_load_3d(smem + b * (N * W) + i * (BOXR * W), &pa.tmap, &bars[b], zt * (2 * W), i * BOXR, g.outer0 + outer);
+    };
+    if (tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+        }
+        __syncthreads();
+    }
+#else
+    const bool tma = false;
+#endif
     int t = blockIdx.x;
-    if (t < ntiles) issue(smem, t);
-    cp_async_commit();
+    if (!tma) {
+        if (t < ntiles) issue(smem, t);
+        cp_async_commit();
+    }
+#ifndef PVD_EMULATE
+    else if (t < ntiles && threadIdx.x == 0) issue_tma(0, t);
+#endif
     int cur = 0;
     for (; t < ntiles; t += gridDim.x) {
         const int tn = t + gridDim.x;
-        if (tn < ntiles) issue(smem + (cur ^ 1) * (N * W), tn);
-        cp_async_commit();
+        if (!tma) {
+            if (tn < ntiles) issue(smem + (cur ^ 1) * (N * W), tn);
+            cp_async_commit();
+        }
+#ifndef PVD_EMULATE
+        else if (tn < ntiles && threadIdx.x == 0) issue_tma(cur ^ 1, tn);
+#endif
         int zt;
         const long long base = tile_base(t, zt);
         const bool wok = wl < g.nzf - zt * W;
@@ -112,8 +161,23 @@ __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const ColPipeArgs p
                                                                   : make_float2(0.f, 0.f);
             }
         }
-        cp_async_wait<1>();  // everything but the prefetch just issued has landed
-        __syncthreads();
+        if (!tma) {
+            cp_async_wait<1>();  // everything but the prefetch just issued has landed
+            __syncthreads();
+        }
+#ifndef PVD_EMULATE
+        else {
+            const unsigned ph = cur ? ph1 : ph0;
+            const long long t0 = clock64();
+            while (!mbar_try_wait(&bars[cur], ph)) {
+                if (clock64() - t0 > 4000000000LL) {  // ~2 s: a broken descriptor must not hang the GPU
+                    if (threadIdx.x == 0) *pa.error_flag = 2;
+                    break;
+                }
+            }
+            if (cur) ph1 ^= 1; else ph0 ^= 1;
+        }
+#endif
         float2* tile = smem + cur * (N * W);
         auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * W + w]; };
         auto gout = [&](int u, int k, int, int, float2 v) {
@@ -147,6 +211,11 @@ __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const ColPipeArgs p
             else
                 fast_fft<N, W, W, NT, +1, R2, R1, 1, false, false>(rin, gout_rev, tile, twr);
         }
+#ifndef PVD_EMULATE
+        // the exchange stages wrote this buffer through the generic proxy; the bulk copy that refills it writes through
+        // the async proxy: order the two before the barrier that hands the buffer back
+        if (tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
         __syncthreads();  // tile buffer may be refilled by the next iteration's prefetch
         cur ^= 1;
     }

@@ -165,8 +165,11 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
 // Whole transform.  Stage list (R1, R2, R3) with R3 == 1 meaning two stages.  IN_SMEM / OUT_SMEM say
 // whether `in` / `out` address the exchange tile itself (then reads must complete before writes).
 // `tws` = Sched<N,R1,R2,R3> tables.
-template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out, class Hook = NoHook>
-__device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws, Hook&& hook = Hook()) {
+// `hook` runs under the first stage's loads, `hook_last` under the last stage's shared-memory reads.
+template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out, class Hook = NoHook,
+          class HookLast = NoHook>
+__device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws, Hook&& hook = Hook(),
+                                         HookLast&& hook_last = HookLast()) {
     static_assert(R1 * R2 * R3 == N, "radix schedule must multiply to N");
     auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
     auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
@@ -175,9 +178,9 @@ __device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const
     if constexpr (R3 > 1) {
         fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1);
         __syncthreads();
-        fast_stage<N, W, NT, R3, R1 * R2, DIR, OUT_SMEM>(sm_in, out, tws);
+        fast_stage<N, W, NT, R3, R1 * R2, DIR, OUT_SMEM>(sm_in, out, tws, hook_last);
     } else {
-        fast_stage<N, W, NT, R2, R1, DIR, OUT_SMEM>(sm_in, out, tws);
+        fast_stage<N, W, NT, R2, R1, DIR, OUT_SMEM>(sm_in, out, tws, hook_last);
     }
 }
 
@@ -281,14 +284,36 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
                 for (int r = threadIdx.x; r < n_in; r += NT) prefetch_l2(in0 + (size_t)r * es);
             }
         };
-        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, rout, tile, tws, pf_hook);
+        // PVD_SPEC_PRE spectrum values per butterfly are requested while the last forward stage is still reading its
+        // inputs from shared memory, so their DRAM round trip runs under the radix butterfly instead of after it
+#ifndef PVD_SPEC_PRE
+#define PVD_SPEC_PRE 0
+#endif
+        constexpr int PRE = (PVD_SPEC_PRE < RL) ? PVD_SPEC_PRE : RL;
         const float2* sp = opaque(g.spec + base + (size_t)b0 * es + wl);
+        float2 spre[BPTL][PRE > 0 ? PRE : 1];
+        auto sp_hook = [&]() {
+            if constexpr (PRE > 0) {
+                PVD_UNROLL
+                for (int u = 0; u < BPTL; ++u) {
+                    PVD_UNROLL
+                    for (int k = 0; k < PRE; ++k)
+                        spre[u][k] = (wok && b0 + u * TPC < LS_::STEP) ? ldg64_ro(eptr(sp, esb, u * TPC + LS_::STEP * k)) : make_float2(0.f, 0.f);
+                }
+            }
+        };
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, rout, tile, tws, pf_hook, sp_hook);
         PVD_UNROLL
         for (int u = 0; u < BPTL; ++u) {
             if (b0 + u * TPC < LS_::STEP) {
                 PVD_UNROLL
-                for (int k = 0; k < RL; ++k)
-                    if (wok) hold[u][k] = cmul(hold[u][k], ldg64_ro(eptr(sp, esb, u * TPC + LS_::STEP * k)));
+                for (int k = 0; k < RL; ++k) {
+                    if (k < PRE) {
+                        hold[u][k] = cmul(hold[u][k], spre[u][k]);
+                    } else if (wok) {
+                        hold[u][k] = cmul(hold[u][k], ldg64_ro(eptr(sp, esb, u * TPC + LS_::STEP * k)));
+                    }
+                }
             }
         }
         __syncthreads();  // every thread finished reading the tile in the last forward stage

@@ -117,6 +117,12 @@ int pvd_plan_destroy(pvd_plan* plan);
 int pvd_plan_set_profiling(pvd_plan* plan, int enable);
 int pvd_plan_get_pass_times(pvd_plan* plan, float* ms, double* hbm_bytes, const char** names, int cap);
 
+/* Device-side watchdogs: the kernels that wait on a TMA bulk copy (direct convolution, y passes) give up after
+ * ~2 s and raise a flag in the workspace instead of hanging the GPU on a bad descriptor.  This call synchronises
+ * `stream`, reads the flags and returns PVD_OK or PVD_ERR_CUDA (text in pvd_last_error()); the results of an
+ * execute whose flag is raised are invalid.  The reference has no counterpart (NumPy raises synchronously). */
+int pvd_plan_check_device_errors(pvd_plan* plan, void* stream);
+
 /* ---- A5/A6/A10: dose voxel kernel evaluated on the image grid ----
  * Device evaluation of the radial dose-point-kernel form shared by the reference's generators
  * (Y90KernelGenerator.generate_kernel data/dose_kernels/y90_kernel.py:20-55,93-140;

@@ -22,7 +22,7 @@ MAX_T = 16
 # every symbol include/pvdose.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "pvd_version", "pvd_last_error", "pvd_good_fft_size", "pvd_good_fft_size_axis", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
-    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times",
+    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
     "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
     "pvd_density_scale", "pvd_monoexp_fit", "pvd_ct_prepare", "pvd_roi_minmax", "pvd_dvh_histogram",
 ]
@@ -85,6 +85,7 @@ class PvdLib:
         d.pvd_plan_destroy.argtypes = [vp]
         d.pvd_plan_set_profiling.argtypes = [vp, C.c_int]
         d.pvd_plan_get_pass_times.argtypes = [vp, fp, C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.c_int]
+        d.pvd_plan_check_device_errors.argtypes = [vp, vp]
         d.pvd_kernel_eval_radial.argtypes = [C.POINTER(RadialModel), C.POINTER(C.c_double), ip, vp, vp]
         d.pvd_hu_to_density_f32.argtypes = [vp, fp, C.c_int, vp, C.c_size_t, vp]
         d.pvd_hu_to_density_i16.argtypes = [vp, fp, C.c_int, vp, C.c_size_t, vp]
@@ -154,6 +155,10 @@ class PvdLib:
         if n < 0:
             self.check(n)
         return [(names[i].decode(), float(ms[i]), float(by[i])) for i in range(n)]
+
+    def plan_check_device_errors(self, plan: int, stream: int = 0):
+        """Synchronise `stream` and raise if a device-side TMA watchdog fired (see include/pvdose.h)."""
+        self.check(self.dll.pvd_plan_check_device_errors(plan, stream))
 
     def kernel_eval_radial(self, beta_terms, photon_terms, scaling: float, spacing, grid, out_ptr: int, stream: int = 0):
         """beta_terms: [(range_mm, amplitude)], photon_terms: [(mu_per_cm, amplitude)]."""

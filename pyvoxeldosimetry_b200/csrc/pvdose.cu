@@ -898,6 +898,22 @@ int pvd_plan_get_pass_times(pvd_plan* p, float* ms, double* hbm_bytes, const cha
     return n;
 }
 
+int pvd_plan_check_device_errors(pvd_plan* p, void* stream_) {
+    if (!p) return fail(PVD_ERR_INVALID, "null argument");
+    if (!p->ws) return fail(PVD_ERR_STATE, "workspace not set");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int flags[2] = {0, 0};
+    cudaMemcpyAsync(flags, p->flag(), sizeof flags, cudaMemcpyDeviceToHost, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) {
+        PVD_CUDA_CHECK("device error flags");
+        return fail(PVD_ERR_CUDA, "device error flags: stream synchronise failed");
+    }
+    if (p->algo == PVD_ALGO_DIRECT && flags[0] != 0)
+        return fail(PVD_ERR_CUDA, "direct convolution: a TMA tile load never completed (flag %d)", flags[0]);
+    if (flags[1] != 0) return fail(PVD_ERR_CUDA, "column pass: a TMA tile load never completed (flag %d)", flags[1]);
+    return PVD_OK;
+}
+
 int pvd_plan_destroy(pvd_plan* p) {
     if (p && p->ev_made)
         for (int i = 0; i <= PVD_MAX_PASSES; ++i) cudaEventDestroy(p->ev[i]);

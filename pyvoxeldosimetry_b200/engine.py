@@ -129,6 +129,12 @@ class ConvPlan:
                                   rho_ref, rho_min, rho_cut, scale, out.data_ptr(), stream)
         return out
 
+    def check_device_errors(self) -> None:
+        """Synchronise the current stream and raise PvdoseError if a device-side watchdog fired (a TMA tile copy that
+        never completed); results of that execute are then invalid.  Tests and smoke() call it after executing."""
+        with torch.cuda.device(self.device):
+            self.lib.plan_check_device_errors(self.handle, _stream_ptr(self.device))
+
     def close(self) -> None:
         if getattr(self, "handle", None):
             self.lib.plan_destroy(self.handle)

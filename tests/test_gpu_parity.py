@@ -30,7 +30,7 @@ def run_plan(torch, a_list, k, boundary, weights=None, density=None, **kw):
     acts = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev) for a in a_list]
     den = None if density is None else torch.from_numpy(np.ascontiguousarray(density, dtype=np.float32)).to(dev)
     out = plan.execute(acts, weights, den, **kw)
-    torch.cuda.synchronize()
+    plan.check_device_errors()  # synchronises; raises if a TMA watchdog fired
     res = out.cpu().numpy()
     plan.close()
     return res

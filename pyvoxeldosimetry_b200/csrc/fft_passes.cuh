@@ -25,6 +25,7 @@ struct RowFwdArgs {
     long long out_s0, out_s1;  // float2 strides of the work buffer
     int M2, Nh;
     int Llog;  // 2^Llog complex lines (= 2^(Llog+1) real rows) per block
+    int dense; // pipelined kernel: rows of input and work buffer are equally spaced in the linear row index (s0 == n1 * s1)
     const float2* tw;
     Stages st;
 };
@@ -158,6 +159,8 @@ struct RowInvArgs {
     int vec4;  // pipelined kernel: dose/density rows are 16-byte aligned and O2 % 4 == 0 -> 128-bit store phase
     int den_pf;  // pipelined kernel: L2-prefetch a tile's density rows before its inverse transform
     int zero;    // always 0 (the struct is memset): an operand the compiler cannot fold, see the P5 store phase
+    int dense;   // pipelined kernel: no crop offset along axes 0/1 and every row stride pair satisfies s0 == O1 * s1
+    int plain_den;  // pipelined kernel: scale * rho_ref == 1 and rho_cut <= 0 -> dose = v / max(rho, rho_min), 3 instructions per voxel
     const float2* tw;
     Stages st;
 };

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
     const float* __restrict__ in0 = g.in[0];
     const float w0 = 0.5f * g.w[0];  // the 1/2 of the Hermitian split, applied once at the input
     const int n1 = g.n1, n2b = g.n2 * 4;
+    const bool dense = g.dense != 0;  // row address = base + linear row index * row stride: no (x, y) bookkeeping
     // (x, y) of a tile row from the tile's first row: one division per tile instead of one per row
     auto row_xy = [&](int x0, int y0, int rr, int& x, int& y) {
         x = x0;
@@ -73,9 +74,13 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
             const bool valid = row0 + rr < (int)nrows;
             long long off = 0;
             if (valid) {
-                int x, y;
-                row_xy(x0, y0, rr, x, y);
-                off = x * g.in_s0 + y * g.in_s1;
+                if (dense) {
+                    off = (long long)(row0 + rr) * g.in_s1;
+                } else {
+                    int x, y;
+                    row_xy(x0, y0, rr, x, y);
+                    off = x * g.in_s0 + y * g.in_s1;
+                }
             }
             const float* src = in0 + off;
             float* dstp = raw + rr * LSF;
@@ -139,13 +144,20 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
         for (int line = warp; line < W; line += NWARPS) {
             const bool va = row0 + line < (int)nrows, vb = row0 + line + W < (int)nrows;
             if (!va) continue;  // rows are consecutive: b valid implies a valid
-            int x, y;
-            row_xy(x0, y0, line, x, y);
-            float2* __restrict__ dsta = g.out + x * g.out_s0 + y * g.out_s1;
-            float2* __restrict__ dstb = dsta;
-            if (vb) {
-                row_xy(x0, y0, line + W, x, y);
-                dstb = g.out + x * g.out_s0 + y * g.out_s1;
+            float2* __restrict__ dsta;
+            float2* __restrict__ dstb;
+            if (dense) {
+                dsta = g.out + (long long)(row0 + line) * g.out_s1;
+                dstb = vb ? dsta + W * g.out_s1 : dsta;
+            } else {
+                int x, y;
+                row_xy(x0, y0, line, x, y);
+                dsta = g.out + x * g.out_s0 + y * g.out_s1;
+                dstb = dsta;
+                if (vb) {
+                    row_xy(x0, y0, line + W, x, y);
+                    dstb = g.out + x * g.out_s0 + y * g.out_s1;
+                }
             }
             constexpr int KIT = (N / 2 + 1 + 31) / 32;
             PVD_UNROLL
@@ -223,6 +235,8 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
     const int Nh = g.Nh, O1 = g.O1, O2 = g.O2, z_lo = g.z_lo;
     const bool has_den = g.density != nullptr;
     const bool vec4 = g.vec4 != 0;
+    const bool dense = g.dense != 0;          // row address = base + linear row index * row stride
+    const bool plain_den = g.plain_den != 0;  // dose = v / max(rho, rho_min)
     // (x, y) of a tile row from the tile's first row: one division per tile instead of one per row
     auto row_xy = [&](int x0, int y0, int rr, int& x, int& y) {
         x = x0;
@@ -238,9 +252,13 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
             const bool valid = row0 + rr < (int)nrows;
             long long off = 0;
             if (valid) {
-                int x, y;
-                row_xy(x0, y0, rr, x, y);
-                off = (x + g.x_lo) * g.in_s0 + (y + g.y_lo) * g.in_s1;
+                if (dense) {
+                    off = (long long)(row0 + rr) * g.in_s1;
+                } else {
+                    int x, y;
+                    row_xy(x0, y0, rr, x, y);
+                    off = (x + g.x_lo) * g.in_s0 + (y + g.y_lo) * g.in_s1;
+                }
             }
             const float2* src = g.in + off;
             float2* dstp = rawc + rr * LSC;
@@ -310,9 +328,13 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
             for (int i = threadIdx.x; i < 32 * lines_per_row; i += NT) {
                 const int rr = i / lines_per_row, ln = i - rr * lines_per_row;
                 if (r0 + rr < (int)nrows) {
-                    int x, y;
-                    row_xy(px0, py0, rr, x, y);
-                    prefetch_l2(g.density + x * g.den_s0 + y * g.den_s1 + ln * 32);
+                    if (dense) {
+                        prefetch_l2(g.density + (long long)(r0 + rr) * g.den_s1 + ln * 32);
+                    } else {
+                        int x, y;
+                        row_xy(px0, py0, rr, x, y);
+                        prefetch_l2(g.density + x * g.den_s0 + y * g.den_s1 + ln * 32);
+                    }
                 }
             }
         }
@@ -330,12 +352,40 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
         const int x0 = cx, y0 = cy;
         for (int rr = warp; rr < 32; rr += NWARPS) {
             if (row0 + rr >= (int)nrows) continue;
-            int x, y;
-            row_xy(x0, y0, rr, x, y);
-            float* __restrict__ dst = g.out + x * g.out_s0 + y * g.out_s1;
-            const float* __restrict__ dg = has_den ? g.density + x * g.den_s0 + y * g.den_s1 : nullptr;
+            float* __restrict__ dst;
+            const float* __restrict__ dg;
+            if (dense) {
+                dst = g.out + (long long)(row0 + rr) * g.out_s1;
+                dg = has_den ? g.density + (long long)(row0 + rr) * g.den_s1 : nullptr;
+            } else {
+                int x, y;
+                row_xy(x0, y0, rr, x, y);
+                dst = g.out + x * g.out_s0 + y * g.out_s1;
+                dg = has_den ? g.density + x * g.den_s0 + y * g.den_s1 : nullptr;
+            }
             const float* srow = rowbuf + rr * LSA;
-            if (vec4 && has_den) {
+            if (vec4 && has_den && plain_den) {
+                // the common call (scale * rho_ref folded into the input weights by the host, no density cut-off):
+                // max, reciprocal, multiply - half the instructions of the general form below
+                constexpr int QIT = ((N + 3) / 4 + 31) / 32;
+                float4 rho[QIT];
+                PVD_UNROLL
+                for (int i = 0; i < QIT; ++i) {
+                    const int z = 4 * (lane + 32 * i);
+                    rho[i] = (z < O2) ? ldg128_ro(dg + z) : make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+                __syncwarp();  // keep the row's loads in flight together (see below)
+                PVD_UNROLL
+                for (int i = 0; i < QIT; ++i) {
+                    const int z = 4 * (lane + 32 * i);
+                    float4 v = *reinterpret_cast<const float4*>(srow + (z < O2 ? z : 0));
+                    v.x *= fast_rcp(fmaxf(rho[i].x, rho_min));
+                    v.y *= fast_rcp(fmaxf(rho[i].y, rho_min));
+                    v.z *= fast_rcp(fmaxf(rho[i].z, rho_min));
+                    v.w *= fast_rcp(fmaxf(rho[i].w, rho_min));
+                    if (z < O2) stg128(dst + z, v);
+                }
+            } else if (vec4 && has_den) {
                 constexpr int QIT = ((N + 3) / 4 + 31) / 32;
                 float4 rho[QIT];
                 PVD_UNROLL

@@ -310,6 +310,7 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
     a.Llog = p->rowLlog;
     a.tw = p->tw(2);
     a.st = p->st[2];
+    a.dense = (s0 == (long long)ext[1] * s1 && a.out_s0 == (long long)ext[1] * a.out_s1) ? 1 : 0;
     const long long nrows = (long long)ext[0] * ext[1];
     const long long per = 2LL << p->rowLlog;
     const long long nblk = (nrows + per - 1) / per;
@@ -344,6 +345,12 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
     const long long plane = (long long)p->m[1] * p->Sz;
     a.es = axis == 0 ? plane : p->Sz;
     a.os = axis == 0 ? p->Sz : plane;
+    {
+        // TIMING EXPERIMENT ONLY (results are wrong): run each column pass with the OTHER axis' strides to measure how
+        // much of a pass's time is its access pattern (needs m[0] == m[1]; PVD_TMA=0)
+        static const int swap = [] { const char* e = getenv("PVD_SWAP_STRIDES_TEST"); return e ? atoi(e) : 0; }();
+        if (swap && p->m[0] == p->m[1]) std::swap(a.es, a.os);
+    }
     a.outer0 = outer0;
     a.n_in = n_in;
     a.M = p->m[axis];
@@ -798,6 +805,14 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     cudaStream_t stream = (cudaStream_t)stream_;
     if (p->algo == PVD_ALGO_DIRECT) return execute_direct(p, h_act, h_weights, T, density, rho_ref, rho_min, rho_cut, scale, dose, stream);
     const double c = 8.0 * p->Nh;  // bytes of one half-spectrum row
+    // The convolution is linear: the output factor scale * rho_ref rides on the input weights the first pass applies
+    // anyway, so the last pass's epilogue is dose = v / max(rho, rho_min) (3 instructions per voxel instead of 6).
+    float wfold[PVD_MAX_T];
+    const float out_factor = scale * (density ? rho_ref : 1.f);
+    for (int t = 0; t < T; ++t) wfold[t] = (h_weights ? h_weights[t] : 1.f) * out_factor;
+    h_weights = wfold;
+    scale = 1.f;
+    rho_ref = 1.f;
     p->npass = 0;
     p->mark(stream, "P1 rows_fwd (z R2C + time-weighted sum)", 4.0 * T * p->n[0] * p->n[1] * p->n[2] + c * p->n[0] * p->n[1]);
     int rc = launch_rows_fwd(p, h_act, h_weights, T, (long long)p->n[1] * p->n[2], p->n[2], p->n, stream);
@@ -843,6 +858,11 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
         const char* e = getenv("PVD_DEN_PF");  // experiment knob
         a.den_pf = e ? atoi(e) : 1;
     }
+    a.dense = (a.x_lo == 0 && a.y_lo == 0 && a.in_s0 == (long long)a.O1 * a.in_s1 && a.out_s0 == (long long)a.O1 * a.out_s1 &&
+               a.den_s0 == (long long)a.O1 * a.den_s1)
+                  ? 1
+                  : 0;
+    a.plain_den = (density && rho_cut <= 0.f) ? 1 : 0;  // scale * rho_ref == 1 by the folding above
     a.vec4 = (p->on[2] % 4 == 0 && a.out_s0 % 4 == 0 && a.out_s1 % 4 == 0 && ((uintptr_t)dose & 15) == 0 &&
               (!density || (((uintptr_t)density & 15) == 0 && a.den_s0 % 4 == 0 && a.den_s1 % 4 == 0)))
                  ? 1

@@ -65,6 +65,29 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 }
 #endif
 
+#ifndef PVD_EMULATE
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// bulk L2 prefetch of one box (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+// spin on an mbarrier phase with a ~2 s watchdog: a broken descriptor raises *flag instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_guarded(unsigned long long* bar, unsigned phase, int* flag, int code) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, phase)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (threadIdx.x == 0) *flag = code;
+            break;
+        }
+    }
+}
+#endif
+
 // KX > 0: cubic fast path with K0 == KX known at compile time; KX == 0: any K0 <= 9 (runtime loop).
 template <int KZ, int KX>
 __global__ void __launch_bounds__(kDirThreads) direct_conv_kernel(const __grid_constant__ CUtensorMap tmap, const DirectArgs g) {

@@ -11,11 +11,16 @@
 // Volume layout follows the reference's NumPy C order arr[x, y, z] (z contiguous), complex
 // work buffer is [M0][M1][Sz] float2 with Sz = round_up(M2/2+1, 16).
 #pragma once
+#include "direct_conv.cuh"  // CUtensorMap, mbarrier / TMA helpers
 #include "fft_core.cuh"
 
 namespace pvd {
 
 struct RowFwdArgs {
+    // pipelined kernel, TMA staging (use_tma): 2-D map of the dense activity volume, dims (n2 floats, rows), box (N/4, 32)
+    alignas(64) CUtensorMap tmap;
+    int use_tma;
+    int* error_flag;
     const float* in[kMaxT];
     float w[kMaxT];
     int T;
@@ -145,6 +150,12 @@ __global__ void __launch_bounds__(PVD_BLOCK) cols_kernel(const ColArgs g) {
 }
 
 struct RowInvArgs {
+    // pipelined kernel, TMA staging (use_tma): 2-D map of the work buffer as 8-byte elements, dims (Sz, rows), box
+    // (LSC, 32); tmap_den (use_tma_den): 2-D map of the density volume as 8-byte elements for bulk L2 prefetches
+    alignas(64) CUtensorMap tmap;
+    alignas(64) CUtensorMap tmap_den;
+    int use_tma, use_tma_den;
+    int* error_flag;
     const float2* in;
     long long in_s0, in_s1;
     int x_lo, y_lo, z_lo;

@@ -40,16 +40,29 @@ struct RowStage {
 };
 
 template <int N, int NT, int MINB, int R1, int R2, int R3>
-__global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArgs g) {
+__global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const __grid_constant__ RowFwdArgs g) {
     constexpr int W = 16, LS = 17;
     using RS = RowStage<N>;
     constexpr int LSF = RS::LSF, CHR = RS::CHR;
+    // TMA staging: the 32 rows arrive as 4 boxes of N/4 floats x 32 rows, laid out [quarter][row][N/4] (a 100-float row
+    // pitch keeps the line-strided first-stage reads at the same 2-way bank conflicts as the 404-float pitch above)
+    constexpr int QW = N / 4;
+    constexpr bool TMA_OK = (N % 16 == 0) && (QW <= 256) && (32 * N * 4 <= RS::BYTES);
     PVD_DYN_SMEM(float2, smem);
     float2* tile = smem;
     float* raw = reinterpret_cast<float*>(smem + N * LS);
     float2* tws = reinterpret_cast<float2*>(raw + 32 * LSF);
+#ifndef PVD_EMULATE
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tws + Sched<N, R1, R2, R3>::TOTAL);
+    const bool tma = TMA_OK && g.use_tma && ((unsigned)__cvta_generic_to_shared(raw) & 127u) == 0;
+    if (tma && threadIdx.x == 0) mbar_init(bar, 1);
+    unsigned ph = 0;
+#else
+    const bool tma = false;
+#endif
     grid_dep_launch();
     Sched<N, R1, R2, R3>::build(tws, g.tw);  // tables come from the plan's twiddle buffer (complete since plan set-up)
+    if (tma) __syncthreads();                // mbarrier initialised before anyone polls it
     grid_dep_wait();                         // predecessor grid done: its output / our output buffer may be touched now
     const long long nrows = (long long)g.n0 * g.n1;
     const int ntiles = (int)((nrows + 31) / 32);
@@ -108,26 +121,60 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const RowFwdArg
             ++x;
         }
     };
-    if (t < ntiles) issue(t, cx, cy);
-    cp_async_commit();
+#ifndef PVD_EMULATE
+    auto issue_tma = [&](int tt) {  // one thread: 4 box copies, rows [32 tt, 32 tt + 32), out-of-range rows / columns arrive as zeros
+        mbar_expect_tx(bar, 32u * N * 4u);
+        PVD_UNROLL
+        for (int q = 0; q < 4; ++q) tma_load_2d(raw + q * (32 * QW), &g.tmap, bar, q * QW, tt * 32);
+    };
+#endif
+    if (!tma) {
+        if (t < ntiles) issue(t, cx, cy);
+        cp_async_commit();
+    }
+#ifndef PVD_EMULATE
+    else if (t < ntiles && threadIdx.x == 0) issue_tma(t);
+#endif
     const int wl = threadIdx.x % W;
     // line wl packs staged rows wl (re) and wl + 16 (im): row starts are then 20 (mod 32) banks apart for
     // LSF = 404, i.e. 2-way conflicts over the 16 lines of a warp (adjacent rows 2wl, 2wl+1 gave 4-way)
     const float* rawA = raw + wl * LSF;
     const float* rawB = rawA + W * LSF;
+    const float* rawTA = raw + wl * QW;  // TMA layout
+    const float* rawTB = rawTA + W * QW;
     for (; t < ntiles; t += gridDim.x) {
-        cp_async_wait<0>();
+        if (!tma) cp_async_wait<0>();
+#ifndef PVD_EMULATE
+        else {
+            mbar_wait_guarded(bar, ph, g.error_flag, 3);
+            ph ^= 1;
+        }
+#endif
         __syncthreads();  // staged rows of tile t visible; previous tile's split phase finished with `tile`
         auto raw_in = [&](int, int, int idx, int) -> float2 { return make_float2(w0 * rawA[idx], w0 * rawB[idx]); };  // w0 = w/2
+        auto raw_in_tma = [&](int, int j, int idx, int) -> float2 {
+            // quarter of idx: a literal for every slot j whose index range stays inside one quarter
+            constexpr int NBl = N / R1;
+            const int lo = NBl * j, hi = lo + NBl - 1;
+            const int q = (lo / QW == hi / QW) ? lo / QW : idx / QW;
+            const int o = q * (32 * QW - QW) + idx;  // q * 32 * QW + (idx - q * QW)
+            return make_float2(w0 * rawTA[o], w0 * rawTB[o]);
+        };
         auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
         auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
-        fast_stage<N, W, NT, R1, 1, -1, false>(raw_in, sm_out, tws);
+        if (tma) fast_stage<N, W, NT, R1, 1, -1, false>(raw_in_tma, sm_out, tws);
+        else fast_stage<N, W, NT, R1, 1, -1, false>(raw_in, sm_out, tws);
         __syncthreads();  // staging buffer consumed -> refill it with the next tile while the rest runs
         const int tn = t + gridDim.x;
         int nx = cx, ny = cy;
         advance(nx, ny);
-        if (tn < ntiles) issue(tn, nx, ny);
-        cp_async_commit();
+        if (!tma) {
+            if (tn < ntiles) issue(tn, nx, ny);
+            cp_async_commit();
+        }
+#ifndef PVD_EMULATE
+        else if (tn < ntiles && threadIdx.x == 0) issue_tma(tn);
+#endif
         if constexpr (R3 > 1) {
             fast_stage<N, W, NT, R2, R1, -1, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1);
             __syncthreads();

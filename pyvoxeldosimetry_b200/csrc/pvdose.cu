@@ -180,7 +180,7 @@ struct FastRows {
     {                                                                                                      \
         N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>,           \
             rows_fwd_pipe_kernel<N, NT, MINB, R1, R2, R3>, rows_inv_pipe_kernel<N, NT, MINB, R1, R2, R3>,  \
-            (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES + Sched<N, R1, R2, R3>::TOTAL * sizeof(float2) \
+            (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES + Sched<N, R1, R2, R3>::TOTAL * sizeof(float2) + 16 \
     }
 #define PVD_ROWS_NOPIPE(N, NT, R1, R2, R3) \
     { N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>, nullptr, nullptr, 0 }
@@ -249,6 +249,7 @@ struct pvd_plan {
     bool usePipe = true;
     bool pdl = true;  // programmatic dependent launch of the specialised kernels (PVD_PDL=0 turns it off)
     // TMA variant of the persistent y passes: tensor maps over the work buffer (forward: n[1] rows, inverse: m[1] rows)
+    bool tmaRows = false;  // TMA staging in the persistent row passes (PVD_TMA_ROWS=0 off)
     bool tmaCols = false;
     CUtensorMap tmapCols[2];
     int tmapRows[2] = {0, 0};
@@ -288,6 +289,23 @@ struct pvd_plan {
 
 namespace {
 
+#ifndef PVD_EMULATE
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+#endif
+
 int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, int T, long long s0, long long s1,
                     const int ext[3], cudaStream_t stream) {
     RowFwdArgs a;
@@ -319,6 +337,21 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
         ((uintptr_t)in[0] & 15) == 0) {
         const FastRows* f = p->fastRows;
         const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[0]);
+        a.use_tma = 0;
+        a.error_flag = p->flag() + 1;
+#ifndef PVD_EMULATE
+        // TMA staging of the 32-row tiles: a 2-D map of the (dense) activity volume, encoded per call (the pointer is the caller's)
+        if (p->tmaRows && a.dense && f->N % 16 == 0 && f->N / 4 <= 256 && ext[2] % 4 == 0) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)ext[2], (cuuint64_t)nrows};
+            const cuuint64_t gstr[1] = {(cuuint64_t)s1 * 4};
+            const cuuint32_t box[2] = {(cuuint32_t)(f->N / 4), 32};
+            const cuuint32_t estr[2] = {1, 1};
+            if (get_encode_tiled()(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(in[0]), gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                a.use_tma = 1;
+        }
+#endif
         PVD_LAUNCH_PDL(p->pdl, f->fwdPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
         PVD_CUDA_CHECK("rows_fwd_pipe_kernel");
         return PVD_OK;
@@ -494,28 +527,17 @@ int plan_finish(pvd_plan* p) {
     return PVD_OK;
 }
 
-#ifndef PVD_EMULATE
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-#endif
 
 // Tensor maps of the y passes (axis 1) over the work buffer: dims (2*Sz floats, rows, m0 planes), one box = 16
 // frequencies x BOXR rows of one plane.  Rows beyond `rows` are out of bounds = zero filled (the implicit padding).
 void make_col_tensor_maps(pvd_plan* p) {
     p->tmaCols = false;
+    p->tmaRows = false;
 #ifndef PVD_EMULATE
+    {
+        const char* er = getenv("PVD_TMA_ROWS");
+        p->tmaRows = !(er && er[0] == '0') && get_encode_tiled() != nullptr;
+    }
     const char* e = getenv("PVD_TMA");
     if (e && e[0] == '0') return;  // PVD_TMA=0: 16-byte cp.async staging instead (y passes at 512: 0.156 -> 0.150 ms with TMA)
     const FastCols* f = p->fastCols[1];

@@ -261,7 +261,7 @@ __device__ __forceinline__ float den_apply(float v, float rho, float sr, float r
 // copy with 128-bit shared loads, 128-bit density loads and 128-bit dose stores - a quarter of the memory
 // instructions and guards of the element-wise version.  Row r of the tile pairs with row r + 16 in one line.
 template <int N, int NT, int MINB, int R1, int R2, int R3>
-__global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArgs g) {
+__global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const __grid_constant__ RowInvArgs g) {
     constexpr int W = 16, LS = 17;
     using RS = RowStage<N>;
     constexpr int LSC = RS::LSC, CHC = RS::CHC;
@@ -272,8 +272,22 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
     float* rowbuf = reinterpret_cast<float*>(smem);
     float2* rawc = smem + N * LS;  // staged complex rows
     float2* tws = rawc + 32 * LSC;
+    // TMA staging: the 32 half-spectrum rows are ONE box (LSC 8-byte elements x 32 rows) of a 2-D map of the work
+    // buffer; the box lands in exactly the [row][LSC] layout the cp.async path builds.  The density rows of the tile
+    // are pulled into L2 by one bulk prefetch per tile instead of one prefetch instruction per 128-byte line.
+    constexpr bool TMA_OK = LSC <= 256;
+#ifndef PVD_EMULATE
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tws + Sched<N, R1, R2, R3>::TOTAL);
+    const bool tma = TMA_OK && g.use_tma && ((unsigned)__cvta_generic_to_shared(rawc) & 127u) == 0;
+    const bool tma_den = g.use_tma_den != 0;
+    if (tma && threadIdx.x == 0) mbar_init(bar, 1);
+    unsigned ph = 0;
+#else
+    const bool tma = false, tma_den = false;
+#endif
     grid_dep_launch();
     Sched<N, R1, R2, R3>::build(tws, g.tw);
+    if (tma) __syncthreads();  // mbarrier initialised before anyone polls it
     grid_dep_wait();
     const long long nrows = (long long)g.O0 * g.O1;
     const int ntiles = (int)((nrows + 31) / 32);
@@ -332,12 +346,29 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
             ++x;
         }
     };
-    if (t < ntiles) issue_spec(t, cx, cy);
-    cp_async_commit();
+#ifndef PVD_EMULATE
+    auto issue_tma = [&](int tt) {  // one thread, one box: rows [32 tt, 32 tt + 32) of the work buffer; rows past the end arrive as zeros
+        mbar_expect_tx(bar, 32u * LSC * 8u);
+        tma_load_2d(rawc, &g.tmap, bar, 0, tt * 32);
+    };
+#endif
+    if (!tma) {
+        if (t < ntiles) issue_spec(t, cx, cy);
+        cp_async_commit();
+    }
+#ifndef PVD_EMULATE
+    else if (t < ntiles && threadIdx.x == 0) issue_tma(t);
+#endif
     const float sr = g.scale * (has_den ? g.rho_ref : 1.f), rho_min = g.rho_min, rho_cut = g.rho_cut;
     const int wl = threadIdx.x % W;
     for (; t < ntiles; t += gridDim.x) {
-        cp_async_wait<0>();
+        if (!tma) cp_async_wait<0>();
+#ifndef PVD_EMULATE
+        else {
+            mbar_wait_guarded(bar, ph, g.error_flag, 4);
+            ph ^= 1;
+        }
+#endif
         __syncthreads();  // staged rows landed; the previous tile's store phase is done with the tile
         // rebuild the packed Hermitian line Z = A + i*B for each pair of rows (lanes along k)
         for (int line = warp; line < W; line += NWARPS) {
@@ -364,8 +395,18 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const RowInvArg
         const int tn = t + gridDim.x;
         int nx = cx, ny = cy;
         advance(nx, ny);
-        if (tn < ntiles) issue_spec(tn, nx, ny);
-        cp_async_commit();
+        if (!tma) {
+            if (tn < ntiles) issue_spec(tn, nx, ny);
+            cp_async_commit();
+        }
+#ifndef PVD_EMULATE
+        else if (threadIdx.x == 0) {
+            if (tn < ntiles) issue_tma(tn);
+        }
+        if (has_den && g.den_pf && tma_den) {
+            if (threadIdx.x == 32) tma_prefetch_2d(&g.tmap_den, 0, t * 32);  // this tile's 32 density rows -> L2
+        } else
+#endif
         if (has_den && g.den_pf) {
             // the density rows of THIS tile are needed after the inverse transform (~10 us from now): pull their
             // 128-byte lines into L2 now so that the store phase does not wait a full DRAM round trip per row

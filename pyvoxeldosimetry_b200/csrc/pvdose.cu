@@ -894,6 +894,37 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     if (p->fastRows && p->usePipe && p->rowPipeGrid[1] > 0 && nrows < 2000000000LL) {
         const FastRows* f = p->fastRows;
         const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[1]);
+        a.use_tma = a.use_tma_den = 0;
+        a.error_flag = p->flag() + 1;
+#ifndef PVD_EMULATE
+        // TMA staging of the half-spectrum rows (work buffer as 8-byte elements) and bulk L2 prefetch of the density rows
+        const int lsc = (((f->N + 3) / 4) * 4 + 4) / 2;
+        if (p->tmaRows && a.dense && lsc <= 256 && lsc <= p->Sz) {
+            const cuuint32_t estr[2] = {1, 1};
+            {
+                const cuuint64_t gdim[2] = {(cuuint64_t)p->Sz, (cuuint64_t)nrows};
+                const cuuint64_t gstr[1] = {(cuuint64_t)a.in_s1 * 8};
+                const cuuint32_t box[2] = {(cuuint32_t)lsc, 32};
+                if (get_encode_tiled()(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, p->buf(), gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                    a.use_tma = 1;
+            }
+            if (density && a.vec4 && a.O2 / 2 <= 256) {
+                const cuuint64_t gdim[2] = {(cuuint64_t)a.O2 / 2, (cuuint64_t)nrows};
+                const cuuint64_t gstr[1] = {(cuuint64_t)a.den_s1 * 4};
+                const cuuint32_t box[2] = {(cuuint32_t)(a.O2 / 2), 32};
+                if (get_encode_tiled()(&a.tmap_den, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<float*>(density), gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                    a.use_tma_den = 1;
+            }
+        }
+        {
+            static const int den_tma_knob = [] { const char* e = getenv("PVD_TMA_DEN"); return e ? atoi(e) : 1; }();
+            if (!den_tma_knob) a.use_tma_den = 0;
+        }
+#endif
         PVD_LAUNCH_PDL(p->pdl, f->invPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
         PVD_CUDA_CHECK("rows_inv_pipe_kernel");
         p->mark_end(stream);

@@ -31,6 +31,7 @@ struct RowFwdArgs {
     int M2, Nh;
     int Llog;  // 2^Llog complex lines (= 2^(Llog+1) real rows) per block
     int dense; // pipelined kernel: rows of input and work buffer are equally spaced in the linear row index (s0 == n1 * s1)
+    int dense_in;  // the same for the input alone (enough for the TMA staging)
     const float2* tw;
     Stages st;
 };
@@ -155,6 +156,7 @@ struct RowInvArgs {
     alignas(64) CUtensorMap tmap;
     alignas(64) CUtensorMap tmap_den;
     int use_tma, use_tma_den;
+    int tma3d;  // tmap is the 3-D view (Sz, M1, M0) of the work buffer: a tile is the box at (0, y + y_lo, x + x_lo) - cropped outputs, O1 % 32 == 0
     int* error_flag;
     const float2* in;
     long long in_s0, in_s1;

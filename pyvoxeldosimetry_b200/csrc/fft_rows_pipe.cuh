@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_pipe_kernel(const __grid_co
             const bool valid = row0 + rr < (int)nrows;
             long long off = 0;
             if (valid) {
-                if (dense) {
+                if (g.dense_in) {
                     off = (long long)(row0 + rr) * g.in_s1;
                 } else {
                     int x, y;
@@ -347,9 +347,10 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const __grid_co
         }
     };
 #ifndef PVD_EMULATE
-    auto issue_tma = [&](int tt) {  // one thread, one box: rows [32 tt, 32 tt + 32) of the work buffer; rows past the end arrive as zeros
+    auto issue_tma = [&](int tt, int x, int y) {  // one thread, one box: the tile's 32 rows of the work buffer; rows past the end arrive as zeros
         mbar_expect_tx(bar, 32u * LSC * 8u);
-        tma_load_2d(rawc, &g.tmap, bar, 0, tt * 32);
+        if (g.tma3d) tma_load_3d(rawc, &g.tmap, bar, 0, y + g.y_lo, x + g.x_lo);
+        else tma_load_2d(rawc, &g.tmap, bar, 0, tt * 32);
     };
 #endif
     if (!tma) {
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const __grid_co
         cp_async_commit();
     }
 #ifndef PVD_EMULATE
-    else if (t < ntiles && threadIdx.x == 0) issue_tma(t);
+    else if (t < ntiles && threadIdx.x == 0) issue_tma(t, cx, cy);
 #endif
     const float sr = g.scale * (has_den ? g.rho_ref : 1.f), rho_min = g.rho_min, rho_cut = g.rho_cut;
     const int wl = threadIdx.x % W;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const __grid_co
         }
 #ifndef PVD_EMULATE
         else if (threadIdx.x == 0) {
-            if (tn < ntiles) issue_tma(tn);
+            if (tn < ntiles) issue_tma(tn, nx, ny);
         }
         if (has_den && g.den_pf && tma_den) {
             if (threadIdx.x == 32) tma_prefetch_2d(&g.tmap_den, 0, t * 32);  // this tile's 32 density rows -> L2

@@ -328,7 +328,8 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
     a.Llog = p->rowLlog;
     a.tw = p->tw(2);
     a.st = p->st[2];
-    a.dense = (s0 == (long long)ext[1] * s1 && a.out_s0 == (long long)ext[1] * a.out_s1) ? 1 : 0;
+    a.dense_in = (s0 == (long long)ext[1] * s1) ? 1 : 0;
+    a.dense = (a.dense_in && a.out_s0 == (long long)ext[1] * a.out_s1) ? 1 : 0;
     const long long nrows = (long long)ext[0] * ext[1];
     const long long per = 2LL << p->rowLlog;
     const long long nblk = (nrows + per - 1) / per;
@@ -341,7 +342,7 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
         a.error_flag = p->flag() + 1;
 #ifndef PVD_EMULATE
         // TMA staging of the 32-row tiles: a 2-D map of the (dense) activity volume, encoded per call (the pointer is the caller's)
-        if (p->tmaRows && a.dense && f->N % 16 == 0 && f->N / 4 <= 256 && ext[2] % 4 == 0) {
+        if (p->tmaRows && a.dense_in && f->N % 16 == 0 && f->N / 4 <= 256 && ext[2] % 4 == 0) {
             const cuuint64_t gdim[2] = {(cuuint64_t)ext[2], (cuuint64_t)nrows};
             const cuuint64_t gstr[1] = {(cuuint64_t)s1 * 4};
             const cuuint32_t box[2] = {(cuuint32_t)(f->N / 4), 32};
@@ -899,9 +900,10 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
 #ifndef PVD_EMULATE
         // TMA staging of the half-spectrum rows (work buffer as 8-byte elements) and bulk L2 prefetch of the density rows
         const int lsc = (((f->N + 3) / 4) * 4 + 4) / 2;
-        if (p->tmaRows && a.dense && lsc <= 256 && lsc <= p->Sz) {
-            const cuuint32_t estr[2] = {1, 1};
-            {
+        a.tma3d = 0;
+        if (p->tmaRows && lsc <= 256 && lsc <= p->Sz && (a.dense || a.O1 % 32 == 0)) {
+            const cuuint32_t estr[3] = {1, 1, 1};
+            if (a.dense) {
                 const cuuint64_t gdim[2] = {(cuuint64_t)p->Sz, (cuuint64_t)nrows};
                 const cuuint64_t gstr[1] = {(cuuint64_t)a.in_s1 * 8};
                 const cuuint32_t box[2] = {(cuuint32_t)lsc, 32};
@@ -909,6 +911,16 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
                     a.use_tma = 1;
+            } else {  // cropped output (x_lo / y_lo, M1 > O1): a tile never straddles x because 32 divides O1
+                const cuuint64_t gdim[3] = {(cuuint64_t)p->Sz, (cuuint64_t)p->m[1], (cuuint64_t)p->m[0]};
+                const cuuint64_t gstr[2] = {(cuuint64_t)a.in_s1 * 8, (cuuint64_t)a.in_s0 * 8};
+                const cuuint32_t box[3] = {(cuuint32_t)lsc, 32, 1};
+                if (get_encode_tiled()(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p->buf(), gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                    a.use_tma = 1;
+                    a.tma3d = 1;
+                }
             }
             if (density && a.vec4 && a.O2 / 2 <= 256) {
                 const cuuint64_t gdim[2] = {(cuuint64_t)a.O2 / 2, (cuuint64_t)nrows};

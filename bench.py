@@ -450,7 +450,7 @@ def run_ours(args, wl):
         dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
         traffic = None  # dram__bytes_read+write of the whole path from the committed ncu --set full capture (same workload only)
-        tpath = os.path.join(REPO, "profiles", "r01g_dram_traffic_c3.json")
+        tpath = os.path.join(REPO, "profiles", "r01h_dram_traffic_c3.json")
         if args.workload == "c3" and args.boundary == "reference" and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("_whole_path_dram_bytes")
         line = {

@@ -110,8 +110,21 @@ struct NoHook {
 };
 // `hook` runs right after the stage's input reads have been ISSUED (and after the optional barrier), before the first
 // use of the loaded values: the place for work that should overlap the load latency (L2 prefetches of later tiles).
-template <int N, int W, int NT, int R, int S, int DIR, bool SYNC_AFTER_READ, class In, class Out, class Hook = NoHook>
-__device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __restrict__ tws, Hook&& hook = Hook()) {
+// Who runs a stage: the whole CTA (default) or a 256-thread group of it with its own named barrier.
+struct BlockCtx {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+#ifndef PVD_EMULATE
+template <int THREADS>
+struct GroupCtx {
+    int t, id;  // thread index inside the group, barrier id (1..15)
+    __device__ __forceinline__ int tid() const { return t; }
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory"); }
+};
+#endif
+template <int N, int W, int NT, int R, int S, int DIR, bool SYNC_AFTER_READ, class In, class Out, class Hook = NoHook, class Ctx = BlockCtx>
+__device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __restrict__ tws, Hook&& hook = Hook(), Ctx ctx = Ctx()) {
     constexpr int NB = N / R;          // butterflies per line
     constexpr int M = NB / S;
     constexpr int TPC = NT / W;        // butterflies of one line processed concurrently
@@ -119,8 +132,8 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
     constexpr bool GUARD = (NB % TPC) != 0;
     constexpr int RP = tw_row<R>();
     static_assert(N % R == 0 && NB % S == 0 && NT % W == 0, "bad radix schedule");
-    const int w = threadIdx.x % W;
-    const int b0 = threadIdx.x / W;
+    const int w = ctx.tid() % W;
+    const int b0 = ctx.tid() / W;
     float2 a[BPT][R];
     PVD_UNROLL
     for (int u = 0; u < BPT; ++u) {
@@ -130,7 +143,7 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
             for (int j = 0; j < R; ++j) a[u][j] = in(u, j, b + NB * j, w);  // q + S*(p + M*j) == b + NB*j
         }
     }
-    if (SYNC_AFTER_READ) __syncthreads();
+    if (SYNC_AFTER_READ) ctx.sync();
     hook();
     PVD_UNROLL
     for (int u = 0; u < BPT; ++u) {
@@ -167,20 +180,20 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
 // `tws` = Sched<N,R1,R2,R3> tables.
 // `hook` runs under the first stage's loads, `hook_last` under the last stage's shared-memory reads.
 template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out, class Hook = NoHook,
-          class HookLast = NoHook>
+          class HookLast = NoHook, class Ctx = BlockCtx>
 __device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws, Hook&& hook = Hook(),
-                                         HookLast&& hook_last = HookLast()) {
+                                         HookLast&& hook_last = HookLast(), Ctx ctx = Ctx()) {
     static_assert(R1 * R2 * R3 == N, "radix schedule must multiply to N");
     auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
     auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
-    fast_stage<N, W, NT, R1, 1, DIR, IN_SMEM>(in, sm_out, tws, hook);
-    __syncthreads();
+    fast_stage<N, W, NT, R1, 1, DIR, IN_SMEM>(in, sm_out, tws, hook, ctx);
+    ctx.sync();
     if constexpr (R3 > 1) {
-        fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1);
-        __syncthreads();
-        fast_stage<N, W, NT, R3, R1 * R2, DIR, OUT_SMEM>(sm_in, out, tws, hook_last);
+        fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1, NoHook(), ctx);
+        ctx.sync();
+        fast_stage<N, W, NT, R3, R1 * R2, DIR, OUT_SMEM>(sm_in, out, tws, hook_last, ctx);
     } else {
-        fast_stage<N, W, NT, R2, R1, DIR, OUT_SMEM>(sm_in, out, tws, hook_last);
+        fast_stage<N, W, NT, R2, R1, DIR, OUT_SMEM>(sm_in, out, tws, hook_last, ctx);
     }
 }
 

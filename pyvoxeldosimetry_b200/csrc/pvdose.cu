@@ -12,6 +12,7 @@
 #include "fft_fast.cuh"
 #include "fft_pipe.cuh"
 #include "fft_pipe2.cuh"
+#include "fft_conv2.cuh"
 #include "fft_rows_pipe.cuh"
 #include "fft_passes.cuh"
 
@@ -249,6 +250,8 @@ struct pvd_plan {
     bool usePipe = true;
     bool pdl = true;  // programmatic dependent launch of the specialised kernels (PVD_PDL=0 turns it off)
     // TMA variant of the persistent y passes: tensor maps over the work buffer (forward: n[1] rows, inverse: m[1] rows)
+    bool conv2 = false;    // x pass with the TMA-staged spectrum tile (fft_conv2.cuh), 512-point axis only
+    CUtensorMap tmapSpec;
     bool tmaRows = false;  // TMA staging in the persistent row passes (PVD_TMA_ROWS=0 off)
     bool tmaCols = false;
     CUtensorMap tmapCols[2];
@@ -420,6 +423,24 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
         PVD_CUDA_CHECK("cols_pipe_kernel");
         return PVD_OK;
     }
+#ifndef PVD_EMULATE
+    if (axis == 0 && mode == COL_CONV && p->conv2 && p->m[0] == 512 && in == p->buf()) {
+        Conv2Args ca;
+        ca.tmap_spec = p->tmapSpec;
+        ca.c = a;
+        ca.ntz = (p->Nh + 15) / 16;
+        ca.ntiles = ca.ntz * nouter;
+        ca.error_flag = p->flag() + 1;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t smem = (size_t)3 * 512 * 16 * sizeof(float2) + 2 * 512 * sizeof(float2) + 64;
+        const int grid = std::min((ca.ntiles + 1) / 2, sms);
+        PVD_LAUNCH_PDL(false, (cols_conv2_kernel<512, 16, 32>), dim3((unsigned)grid), dim3(512), smem, stream, ca);
+        PVD_CUDA_CHECK("cols_conv2_kernel");
+        return PVD_OK;
+    }
+#endif
     if (p->fastCols[axis]) {
         const FastCols* f = p->fastCols[axis];
         const size_t smem = ((size_t)f->N * 16 + 4 * f->N) * sizeof(float2);
@@ -538,6 +559,23 @@ void make_col_tensor_maps(pvd_plan* p) {
     {
         const char* er = getenv("PVD_TMA_ROWS");
         p->tmaRows = !(er && er[0] == '0') && get_encode_tiled() != nullptr;
+    }
+    p->conv2 = false;
+    {
+        const char* ec = getenv("PVD_P3_DUAL");
+        if (ec && ec[0] == '1' && p->m[0] == 512 && get_encode_tiled()) {
+            memset(&p->tmapSpec, 0, sizeof(CUtensorMap));
+            const cuuint64_t gdim[3] = {(cuuint64_t)2 * p->Sz, (cuuint64_t)p->m[1], (cuuint64_t)p->m[0]};
+            const cuuint64_t gstr[2] = {(cuuint64_t)p->Sz * 8, (cuuint64_t)p->m[1] * p->Sz * 8};
+            const cuuint32_t box[3] = {32, 1, (cuuint32_t)tma_box_rows(512)};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const size_t smem = (size_t)3 * 512 * 16 * sizeof(float2) + 2 * 512 * sizeof(float2) + 64;
+            if (get_encode_tiled()(&p->tmapSpec, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->spec(), gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                cudaFuncSetAttribute(cols_conv2_kernel<512, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+                p->conv2 = true;
+        }
     }
     const char* e = getenv("PVD_TMA");
     if (e && e[0] == '0') return;  // PVD_TMA=0: 16-byte cp.async staging instead (y passes at 512: 0.156 -> 0.150 ms with TMA)

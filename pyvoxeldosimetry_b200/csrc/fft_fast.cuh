@@ -198,21 +198,21 @@ __device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const
 }
 
 // Radix of the last stage and the register-slot geometry of its outputs.
-template <int N, int NT, int R1, int R2, int R3>
+template <int N, int NT, int R1, int R2, int R3, int W = 16>
 struct LastStage {
     static constexpr int RL = (R3 > 1) ? R3 : R2;
     static constexpr int STEP = N / RL;            // output index of slot (u, k) = b0 + u*TPC + STEP*k
-    static constexpr int TPC = NT / 16;
+    static constexpr int TPC = NT / W;
     static constexpr int BPT = (STEP + TPC - 1) / TPC;
 };
 
 // ------------------------------------------------------------------------------------------------
 // Column passes (axis 1 forward / inverse, axis 0 forward * spectrum * inverse, kernel spectrum).
 // One tile per CTA; used where the double-buffered persistent variant (fft_pipe.cuh) does not fit.
-template <int N, int NT, int R1, int R2, int R3, int MODE, int MINB = 1>
+// W = frequencies per tile (16 = full 128-byte lines; 8 = half lines, half the shared memory per CTA: more CTAs per SM).
+template <int N, int NT, int R1, int R2, int R3, int MODE, int MINB = 1, int W = 16>
 __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
-    constexpr int W = 16;
-    using LS_ = LastStage<N, NT, R1, R2, R3>;
+    using LS_ = LastStage<N, NT, R1, R2, R3, W>;
     constexpr int RL = LS_::RL, TPC = LS_::TPC, BPTL = LS_::BPT;
     using Fwd = Sched<N, R1, R2, R3>;
     using Rev = Sched<N, (R3 > 1 ? R3 : R2), (R3 > 1 ? R2 : R1), (R3 > 1 ? R1 : 1)>;

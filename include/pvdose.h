@@ -47,6 +47,9 @@ extern "C" {
 #define PVD_ALGO_AUTO 0
 #define PVD_ALGO_FFT 1    /* hand-written Stockham 3-D real FFT convolution */
 #define PVD_ALGO_DIRECT 2 /* direct tiled convolution, TMA-staged halo tiles (small kernels) */
+#define PVD_ALGO_FFT_UNPIPELINED 3 /* FFT path on the one-tile-per-CTA kernels only: the form the engine falls back to where
+                                      the persistent, TMA-pipelined tiles do not fit one SM's shared memory (lengths 864,
+                                      1024, 1152); selectable so that validation can cover it at any size */
 
 #define PVD_MAX_T 16 /* activity volumes fused into one execute call */
 

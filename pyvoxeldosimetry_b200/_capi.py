@@ -16,7 +16,7 @@ DEFAULT_LIB = os.path.join(HERE, "libpvdose.so")
 PVD_OK = 0
 ERR_NAMES = {-1: "PVD_ERR_INVALID", -2: "PVD_ERR_CUDA", -3: "PVD_ERR_STATE", -4: "PVD_ERR_NONFINITE", -5: "PVD_ERR_UNSUPPORTED"}
 BOUNDARY_REFERENCE, BOUNDARY_SAME = 0, 1
-ALGO_AUTO, ALGO_FFT, ALGO_DIRECT = 0, 1, 2
+ALGO_AUTO, ALGO_FFT, ALGO_DIRECT, ALGO_FFT_UNPIPELINED = 0, 1, 2, 3
 MAX_T = 16
 
 # every symbol include/pvdose.h declares (checked by tests/test_capi_symbols.py)

@@ -6,6 +6,12 @@ package rebuilds).  Dead branches of the reference are repaired (SURVEY.md secti
   * `tissue_densities` is honoured (voxel-wise density correction fused into the last FFT pass);
   * a single time point fills `absorbed_dose` with the physical-decay integral of the dose rate
     (so examples/single_timepoint_y90_physical_decay.py runs) unless strict_reference is set.
+Time units (recorded in result.metadata['time_unit_of_integration']): 'activity' mode integrates in the CALLER's unit
+(hours by default: activity_sampler.py:74-78 applies no conversion, so do we), 'dose_rate' mode and the single-timepoint
+physical-decay dose integrate in SECONDS (the x3600 of kernel_convolution.py:102) - the same inputs differ by the
+unit factor between the modes, as they would in the reference had its missing methods existed.
+In 'activity' mode result.dose_rate_maps is filled (T extra convolutions) because the reference's own example indexes
+it (examples/time_integrated_dose.py:110); config['return_dose_rate_maps'] = False restores the reference's [].
 Image registration (SimpleITK, core/image_registration.py) is out of scope: maps are taken as aligned
 unless the caller supplies config['registration'] = callable(fixed, moving, spacing) -> aligned.
 """
@@ -79,11 +85,13 @@ class DoseCalculator:
                     # the reference returns [] here yet its own example plots result.dose_rate_maps[i]
                     # (examples/time_integrated_dose.py:110); on the GPU the T extra convolutions are cheap
                     rates = [calc.calculate_dose_rate(a, voxel_size, tissue_densities) for a in maps]
-                return DoseCalculationResult(dose, rates, time_points, {"mode": "multi_timepoint_activity"})
+                return DoseCalculationResult(dose, rates, time_points, {"mode": "multi_timepoint_activity",
+                                                                        "time_unit_of_integration": self.activity_sampler.units})
             if integration_mode == "dose_rate":
                 rates = [calc.calculate_dose_rate(a, voxel_size, tissue_densities) for a in maps]
                 dose = self.activity_sampler.integrate_dose_rates(rates, time_points, integration_limit)
-                return DoseCalculationResult(dose, rates, time_points, {"mode": "multi_timepoint_doserate"})
+                return DoseCalculationResult(dose, rates, time_points, {"mode": "multi_timepoint_doserate",
+                                                                        "time_unit_of_integration": "seconds"})
             raise ValueError(f"Unknown integration_mode: {integration_mode}")
 
         if activity_maps is not None and len(activity_maps) == 1:
@@ -97,7 +105,8 @@ class DoseCalculator:
                 if self.config.get("decay_correct_to_t0") and time_points:
                     factor *= math.exp(math.log(2.0) * float(time_points[0]) / self.activity_sampler.half_life)
                 absorbed = rate * np.float32(factor) if rate.dtype == np.float32 else rate * factor
-            return DoseCalculationResult(absorbed, [rate], time_points or [], {"mode": "single_timepoint"})
+            return DoseCalculationResult(absorbed, [rate], time_points or [], {"mode": "single_timepoint",
+                                                                             "time_unit_of_integration": "seconds"})
 
         raise ValueError("Invalid input for dose calculation.")
 

@@ -63,6 +63,7 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         self._kernel_host: Optional[np.ndarray] = None
         self._kernel_dev: Optional[torch.Tensor] = None
         self._aniso_kernels: Dict[tuple, torch.Tensor] = {}
+        self._kernel_user = False
         self._load_dose_kernel()
 
     # ------------------------------------------------------------------ kernel state
@@ -71,13 +72,19 @@ class KernelConvolutionCalculator(DosimetryCalculator):
             nuclide=self.radionuclide, tissue_type=self.tissue_name, voxel_size=self.kernel_resolution,
             grid_size=self.kernel_grid, device=self.device)
         self._kernel_host = None
+        self._kernel_user = False
+        self._aniso_kernels.clear()
         self._kernel_version += 1
 
     @property
     def kernel(self) -> np.ndarray:
-        """Public, assignable kernel (the reference exposes ``self.kernel`` as mutable state)."""
+        """Public, assignable kernel (the reference exposes ``self.kernel`` as mutable state).  The returned array is a
+        read-only host copy: in-place edits would never reach the device, so they raise instead of being lost -
+        assign a new array (``calc.kernel = k``) to change the kernel."""
         if self._kernel_host is None:
-            self._kernel_host = self._kernel_dev.cpu().numpy().astype(np.float64)
+            host = self._kernel_dev.cpu().numpy().astype(np.float64)
+            host.setflags(write=False)
+            self._kernel_host = host
         return self._kernel_host
 
     @kernel.setter
@@ -85,12 +92,16 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         arr = np.asarray(value)
         if arr.ndim != 3:
             raise ValueError("kernel must be a 3-D array")
-        self._kernel_host = arr
+        host = np.array(arr, dtype=np.float64)  # private copy: later edits of the caller's array do not alias the device kernel
+        host.setflags(write=False)
+        self._kernel_host = host
         self._kernel_dev = engine.to_device_f32(arr, self.device)
+        self._kernel_user = True   # a caller-supplied kernel is taken as sampled on the image grid, whatever voxel_size says
+        self._aniso_kernels.clear()
         self._kernel_version += 1  # cached spectra are rebuilt on next use
 
     def _kernel_for(self, voxel_size) -> Tuple[torch.Tensor, object]:
-        if voxel_size is None or _same_spacing(voxel_size, self.kernel_resolution):
+        if voxel_size is None or self._kernel_user or _same_spacing(voxel_size, self.kernel_resolution):
             return self._kernel_dev, ("k", self._kernel_version)
         if len(tuple(voxel_size)) != 3:
             raise ValueError("voxel_size must be a tuple of length 3.")
@@ -133,6 +144,7 @@ class KernelConvolutionCalculator(DosimetryCalculator):
             raise ValueError("All activity maps must have the same dimensions")
         kdev, tag = self._kernel_for(voxel_size)
         plan = self._plans.get(shape, tuple(kdev.shape), self.boundary, self.device, tag, lambda: kdev, self.algo)
+        self._last_plan = plan
         acts = [engine.to_device_f32(m, self.device) for m in maps]
         den = None
         if tissue_densities is not None and ct_hu is not None:
@@ -153,9 +165,19 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         if out is not None:
             tgt = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
             tgt.copy_(dose, non_blocking=False)
+            self._check_device_errors()
             return out if not isinstance(out, torch.Tensor) else out.numpy()
         host = dose.cpu().numpy()
+        self._check_device_errors()
         return host.astype(np.float64) if want64 else host
+
+    def _check_device_errors(self) -> None:
+        """Every host-returning path ends here: read (and clear) the device-side TMA watchdog flags of the plans this
+        calculator has used and raise PvdoseError rather than hand back a dose map computed from a tile that never
+        arrived.  Device-tensor-returning calls stay asynchronous: call this after your own synchronisation."""
+        plan = getattr(self, "_last_plan", None)
+        if plan is not None and plan.handle:
+            plan.check_device_errors()
 
     # ------------------------------------------------------------------ reference API
     def calculate_dose_rate(self, activity_map, voxel_size: Tuple[float, float, float] = None,
@@ -269,6 +291,7 @@ class KernelConvolutionCalculator(DosimetryCalculator):
                 results.append(tgt)
         for s in (s_in, s_cmp, s_out):
             s.synchronize()
+        plan.check_device_errors()
         return [r.numpy() for r in results]
 
     def _lib_hu_to_density(self, hu: torch.Tensor, knots, rho: torch.Tensor) -> None:

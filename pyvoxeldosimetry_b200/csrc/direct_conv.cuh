@@ -21,6 +21,9 @@ struct CUtensorMap { unsigned long long opaque[16]; };
 
 namespace pvd {
 
+// Device-side watchdog of every TMA wait (~10 s at 1.9 GHz): a transaction that never completes (bad descriptor) raises a
+// flag in the workspace instead of hanging the GPU; the host API reads and clears the flag on every host-returning path.
+constexpr long long kWatchdogCycles = 20000000000LL;
 constexpr int kDirTX = 8, kDirTY = 8, kDirTZ = 64, kDirThreads = 256;
 
 struct DirectArgs {
@@ -76,11 +79,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
-// spin on an mbarrier phase with a ~2 s watchdog: a broken descriptor raises *flag instead of hanging the GPU
+// spin on an mbarrier phase with a ~10 s watchdog: a broken descriptor raises *flag instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_guarded(unsigned long long* bar, unsigned phase, int* flag, int code) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, phase)) {
-        if (clock64() - t0 > 4000000000LL) {
+        if (clock64() - t0 > kWatchdogCycles) {
             if (threadIdx.x == 0) *flag = code;
             break;
         }
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(kDirThreads) direct_conv_kernel(const __grid_c
     {
         const long long t0 = clock64();
         while (!mbar_try_wait(bar, 0)) {
-            if (clock64() - t0 > 4000000000LL) {  // ~2 s: a broken descriptor must not hang the GPU
+            if (clock64() - t0 > kWatchdogCycles) {  // ~10 s: a broken descriptor must not hang the GPU
                 if (tid == 0) *g.error_flag = 1;
                 break;
             }

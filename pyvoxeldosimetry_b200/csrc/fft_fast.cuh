@@ -105,11 +105,6 @@ struct Sched {
 
 // One Stockham DIF stage with radix R and stride S.  in(u, j, idx, w) -> float2, out(u, k, idx, w, v).
 // (u, j)/(u, k) are the register slots (compile-time after unrolling), idx the transform index, w the line.
-struct NoHook {
-    __device__ __forceinline__ void operator()() const {}
-};
-// `hook` runs right after the stage's input reads have been ISSUED (and after the optional barrier), before the first
-// use of the loaded values: the place for work that should overlap the load latency (L2 prefetches of later tiles).
 // Who runs a stage: the whole CTA (default) or a 256-thread group of it with its own named barrier.
 struct BlockCtx {
     __device__ __forceinline__ int tid() const { return threadIdx.x; }
@@ -123,8 +118,8 @@ struct GroupCtx {
     __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory"); }
 };
 #endif
-template <int N, int W, int NT, int R, int S, int DIR, bool SYNC_AFTER_READ, class In, class Out, class Hook = NoHook, class Ctx = BlockCtx>
-__device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __restrict__ tws, Hook&& hook = Hook(), Ctx ctx = Ctx()) {
+template <int N, int W, int NT, int R, int S, int DIR, bool SYNC_AFTER_READ, class In, class Out, class Ctx = BlockCtx>
+__device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __restrict__ tws, Ctx ctx = Ctx()) {
     constexpr int NB = N / R;          // butterflies per line
     constexpr int M = NB / S;
     constexpr int TPC = NT / W;        // butterflies of one line processed concurrently
@@ -144,7 +139,6 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
         }
     }
     if (SYNC_AFTER_READ) ctx.sync();
-    hook();
     PVD_UNROLL
     for (int u = 0; u < BPT; ++u) {
         const int b = b0 + u * TPC;
@@ -178,22 +172,19 @@ __device__ __forceinline__ void fast_stage(In&& in, Out&& out, const float2* __r
 // Whole transform.  Stage list (R1, R2, R3) with R3 == 1 meaning two stages.  IN_SMEM / OUT_SMEM say
 // whether `in` / `out` address the exchange tile itself (then reads must complete before writes).
 // `tws` = Sched<N,R1,R2,R3> tables.
-// `hook` runs under the first stage's loads, `hook_last` under the last stage's shared-memory reads.
-template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out, class Hook = NoHook,
-          class HookLast = NoHook, class Ctx = BlockCtx>
-__device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws, Hook&& hook = Hook(),
-                                         HookLast&& hook_last = HookLast(), Ctx ctx = Ctx()) {
+template <int N, int W, int LS, int NT, int DIR, int R1, int R2, int R3, bool IN_SMEM, bool OUT_SMEM, class In, class Out, class Ctx = BlockCtx>
+__device__ __forceinline__ void fast_fft(In&& in, Out&& out, float2* tile, const float2* __restrict__ tws, Ctx ctx = Ctx()) {
     static_assert(R1 * R2 * R3 == N, "radix schedule must multiply to N");
     auto sm_in = [&](int, int, int idx, int w) -> float2 { return tile[idx * LS + w]; };
     auto sm_out = [&](int, int, int idx, int w, float2 v) { tile[idx * LS + w] = v; };
-    fast_stage<N, W, NT, R1, 1, DIR, IN_SMEM>(in, sm_out, tws, hook, ctx);
+    fast_stage<N, W, NT, R1, 1, DIR, IN_SMEM>(in, sm_out, tws, ctx);
     ctx.sync();
     if constexpr (R3 > 1) {
-        fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1, NoHook(), ctx);
+        fast_stage<N, W, NT, R2, R1, DIR, true>(sm_in, sm_out, tws + Sched<N, R1, R2, R3>::T1, ctx);
         ctx.sync();
-        fast_stage<N, W, NT, R3, R1 * R2, DIR, OUT_SMEM>(sm_in, out, tws, hook_last, ctx);
+        fast_stage<N, W, NT, R3, R1 * R2, DIR, OUT_SMEM>(sm_in, out, tws, ctx);
     } else {
-        fast_stage<N, W, NT, R2, R1, DIR, OUT_SMEM>(sm_in, out, tws, hook_last, ctx);
+        fast_stage<N, W, NT, R2, R1, DIR, OUT_SMEM>(sm_in, out, tws, ctx);
     }
 }
 
@@ -269,64 +260,16 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(const ColArgs g) {
     } else if constexpr (MODE == COL_INV) {
         fast_fft<N, W, W, NT, +1, R1, R2, R3, true, false>(gin, gout, tile, tws);
     } else {  // COL_CONV: forward -> * spectrum -> inverse, the middle never leaves registers
-        // L2 prefetch (no registers held): the spectrum lines this CTA multiplies by after its forward transform, and
-        // the input lines of the tile that the CTA scheduled into this slot next will most likely get (blocks are
-        // dispatched in linear order, pf_dist = CTAs resident on the whole GPU) - their first-stage loads then hit L2.
-        if (g.pf_dist != 0) {  // pf_dist < 0: spectrum lines only
-            const float2* sp0 = g.spec + base;
-            for (int r = threadIdx.x; r < g.M; r += NT) prefetch_l2(sp0 + (size_t)r * es);
-            const long long nxt = (long long)blockIdx.y * gridDim.x + blockIdx.x + g.pf_dist;
-            const long long ny = nxt / gridDim.x, nx = nxt - ny * gridDim.x;
-            if (g.pf_dist > 0 && ny < gridDim.y) {
-                const float2* in0 = g.in + (long long)(g.outer0 + (int)ny) * g.os + nx * W;
-                for (int r = threadIdx.x; r < n_in; r += NT) prefetch_l2(in0 + (size_t)r * es);
-            }
-        }
         float2 hold[BPTL][RL];
         auto rout = [&](int u, int k, int, int, float2 v) { hold[u][k] = v; };
-        // tile walk: while this tile's first-stage loads are in flight, pull this tile's spectrum lines (bit 1 of
-        // loop_pf) and the input lines of the tile this CTA processes next (bit 0) into L2
-        auto pf_hook = [&]() {
-            if (g.loop_pf & 2) {
-                const float2* sp0 = g.spec + base;
-                for (int r = threadIdx.x; r < g.M; r += NT) prefetch_l2(sp0 + (size_t)r * es);
-            }
-            if ((g.loop_pf & 1) && t + tstep < tend) {
-                const int tn = t + tstep, on = tn / g.loop_ntz, zn = tn - on * g.loop_ntz;
-                const float2* in0 = g.in + (long long)(g.outer0 + on) * g.os + zn * W;
-                for (int r = threadIdx.x; r < n_in; r += NT) prefetch_l2(in0 + (size_t)r * es);
-            }
-        };
-        // PVD_SPEC_PRE spectrum values per butterfly are requested while the last forward stage is still reading its
-        // inputs from shared memory, so their DRAM round trip runs under the radix butterfly instead of after it
-#ifndef PVD_SPEC_PRE
-#define PVD_SPEC_PRE 0
-#endif
-        constexpr int PRE = (PVD_SPEC_PRE < RL) ? PVD_SPEC_PRE : RL;
         const float2* sp = opaque(g.spec + base + (size_t)b0 * es + wl);
-        float2 spre[BPTL][PRE > 0 ? PRE : 1];
-        auto sp_hook = [&]() {
-            if constexpr (PRE > 0) {
-                PVD_UNROLL
-                for (int u = 0; u < BPTL; ++u) {
-                    PVD_UNROLL
-                    for (int k = 0; k < PRE; ++k)
-                        spre[u][k] = (wok && b0 + u * TPC < LS_::STEP) ? ldg64_ro(eptr(sp, esb, u * TPC + LS_::STEP * k)) : make_float2(0.f, 0.f);
-                }
-            }
-        };
-        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, rout, tile, tws, pf_hook, sp_hook);
+        fast_fft<N, W, W, NT, -1, R1, R2, R3, true, false>(gin, rout, tile, tws);
         PVD_UNROLL
         for (int u = 0; u < BPTL; ++u) {
             if (b0 + u * TPC < LS_::STEP) {
                 PVD_UNROLL
-                for (int k = 0; k < RL; ++k) {
-                    if (k < PRE) {
-                        hold[u][k] = cmul(hold[u][k], spre[u][k]);
-                    } else if (wok) {
-                        hold[u][k] = cmul(hold[u][k], ldg64_ro(eptr(sp, esb, u * TPC + LS_::STEP * k)));
-                    }
-                }
+                for (int k = 0; k < RL; ++k)
+                    if (wok) hold[u][k] = cmul(hold[u][k], ldg64_ro(eptr(sp, esb, u * TPC + LS_::STEP * k)));
             }
         }
         __syncthreads();  // every thread finished reading the tile in the last forward stage

@@ -100,8 +100,6 @@ struct ColArgs {
     int Wlog;           // tile width 2^Wlog frequencies
     int mode;
     float scale;
-    int pf_dist;  // one-tile-per-CTA kernels: L2-prefetch the tile of block (linear id + pf_dist); 0 = off
-    int loop_pf;  // tile walk: L2 prefetch mask (1: next tile's input lines, 2: this tile's spectrum lines)
     int loop_ntz, loop_ntiles;  // cols_fast_kernel as a persistent 1-D grid: tiles along the frequency axis / in total (0: 2-D grid, one tile per CTA)
     const float2* tw;
     Stages st;
@@ -170,8 +168,6 @@ struct RowInvArgs {
     int M2, Nh;
     int Llog;
     int vec4;  // pipelined kernel: dose/density rows are 16-byte aligned and O2 % 4 == 0 -> 128-bit store phase
-    int den_pf;  // pipelined kernel: L2-prefetch a tile's density rows before its inverse transform
-    int zero;    // always 0 (the struct is memset): an operand the compiler cannot fold, see the P5 store phase
     int dense;   // pipelined kernel: no crop offset along axes 0/1 and every row stride pair satisfies s0 == O1 * s1
     int plain_den;  // pipelined kernel: scale * rho_ref == 1 and rho_cut <= 0 -> dose = v / max(rho, rho_min), 3 instructions per voxel
     const float2* tw;

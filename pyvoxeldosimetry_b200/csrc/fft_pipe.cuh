@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const __grid_consta
             const unsigned ph = cur ? ph1 : ph0;
             const long long t0 = clock64();
             while (!mbar_try_wait(&bars[cur], ph)) {
-                if (clock64() - t0 > 4000000000LL) {  // ~2 s: a broken descriptor must not hang the GPU
+                if (clock64() - t0 > kWatchdogCycles) {  // ~10 s: a broken descriptor must not hang the GPU
                     if (threadIdx.x == 0) *pa.error_flag = 2;
                     break;
                 }

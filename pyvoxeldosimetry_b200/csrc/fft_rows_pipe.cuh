@@ -404,11 +404,11 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_pipe_kernel(const __grid_co
         else if (threadIdx.x == 0) {
             if (tn < ntiles) issue_tma(tn, nx, ny);
         }
-        if (has_den && g.den_pf && tma_den) {
+        if (has_den && tma_den) {
             if (threadIdx.x == 32) tma_prefetch_2d(&g.tmap_den, 0, t * 32);  // this tile's 32 density rows -> L2
         } else
 #endif
-        if (has_den && g.den_pf) {
+        if (has_den) {
             // the density rows of THIS tile are needed after the inverse transform (~10 us from now): pull their
             // 128-byte lines into L2 now so that the store phase does not wait a full DRAM round trip per row
             const int r0 = t * 32;

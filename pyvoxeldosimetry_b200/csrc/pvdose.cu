@@ -11,8 +11,6 @@
 #include "analysis.cuh"
 #include "fft_fast.cuh"
 #include "fft_pipe.cuh"
-#include "fft_pipe2.cuh"
-#include "fft_conv2.cuh"
 #include "fft_rows_pipe.cuh"
 #include "fft_passes.cuh"
 
@@ -167,14 +165,6 @@ struct FastRows {
              cols_pipe_kernel<N, NTC, 1, R1, R2, R3, COL_CONV>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC>}, \
             {NT, NT, NTC, NT}, {NT, NT, NT, NT}                                                                 \
     }
-// persistent variant with two columns per thread (fft_pipe2.cuh)
-#define PVD_COLS_P2(N, NT, MINB, R1, R2, R3)                                                                        \
-    {                                                                                                               \
-        N, NT, PVD_COLS_FN(N, NT, R1, R2, R3),                                                                      \
-            {cols_pipe2_kernel<N, NT, MINB, R1, R2, R3, COL_FWD>, cols_pipe2_kernel<N, NT, MINB, R1, R2, R3, COL_INV>, \
-             cols_pipe2_kernel<N, NT, MINB, R1, R2, R3, COL_CONV>, cols_pipe2_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC>}, \
-            {NT, NT, NT, NT}, {NT, NT, NT, NT}                                                                      \
-    }
 #define PVD_COLS_NOPIPE(N, NT, R1, R2, R3) \
     { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), {nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}, {NT, NT, NT, NT} }
 #define PVD_ROWS(N, NT, MINB, R1, R2, R3)                                                                  \
@@ -219,6 +209,13 @@ const FastRows* find_fast_rows(int n) {
     return nullptr;
 }
 
+// The ONE environment hook the library reads (tests only): PVD_FORCE_GENERIC=1 routes every length through the
+// any-length engine of fft_passes.cuh, so the parity tests can cover it at sizes the specialised menu would take.
+bool force_generic() {
+    const char* e = getenv("PVD_FORCE_GENERIC");
+    return e && e[0] == '1';
+}
+
 // Transform length for an axis that needs at least n points: a length on the specialised menu wins when
 // it costs at most 15 % more points than the best generic {2,3,5,7}-smooth length.
 int good_size_axis(int n, int axis) {
@@ -231,8 +228,7 @@ int good_size_axis(int n, int axis) {
         for (const auto& e : kFastCols)
             if (e.N >= n && (best < 0 || e.N < best)) best = e.N;
     }
-    const char* force = getenv("PVD_FORCE_GENERIC");
-    if (force && force[0] == '1') return g;
+    if (force_generic()) return g;
     return (best > 0 && (double)best <= 1.15 * (double)n) ? best : g;
 }
 
@@ -248,11 +244,9 @@ struct pvd_plan {
     const FastCols* fastCols[2] = {nullptr, nullptr};  // size-specialised kernels, when the length is on the menu
     const FastRows* fastRows = nullptr;
     bool usePipe = true;
-    bool pdl = true;  // programmatic dependent launch of the specialised kernels (PVD_PDL=0 turns it off)
+    bool pdl = true;  // programmatic dependent launch of the specialised kernels
     // TMA variant of the persistent y passes: tensor maps over the work buffer (forward: n[1] rows, inverse: m[1] rows)
-    bool conv2 = false;    // x pass with the TMA-staged spectrum tile (fft_conv2.cuh), 512-point axis only
-    CUtensorMap tmapSpec;
-    bool tmaRows = false;  // TMA staging in the persistent row passes (PVD_TMA_ROWS=0 off)
+    bool tmaRows = false;  // TMA staging in the persistent row passes
     bool tmaCols = false;
     CUtensorMap tmapCols[2];
     int tmapRows[2] = {0, 0};
@@ -382,12 +376,6 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
     const long long plane = (long long)p->m[1] * p->Sz;
     a.es = axis == 0 ? plane : p->Sz;
     a.os = axis == 0 ? p->Sz : plane;
-    {
-        // TIMING EXPERIMENT ONLY (results are wrong): run each column pass with the OTHER axis' strides to measure how
-        // much of a pass's time is its access pattern (needs m[0] == m[1]; PVD_TMA=0)
-        static const int swap = [] { const char* e = getenv("PVD_SWAP_STRIDES_TEST"); return e ? atoi(e) : 0; }();
-        if (swap && p->m[0] == p->m[1]) std::swap(a.es, a.os);
-    }
     a.outer0 = outer0;
     a.n_in = n_in;
     a.M = p->m[axis];
@@ -423,44 +411,16 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
         PVD_CUDA_CHECK("cols_pipe_kernel");
         return PVD_OK;
     }
-#ifndef PVD_EMULATE
-    if (axis == 0 && mode == COL_CONV && p->conv2 && p->m[0] == 512 && in == p->buf()) {
-        Conv2Args ca;
-        ca.tmap_spec = p->tmapSpec;
-        ca.c = a;
-        ca.ntz = (p->Nh + 15) / 16;
-        ca.ntiles = ca.ntz * nouter;
-        ca.error_flag = p->flag() + 1;
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const size_t smem = (size_t)3 * 512 * 16 * sizeof(float2) + 2 * 512 * sizeof(float2) + 64;
-        const int grid = std::min((ca.ntiles + 1) / 2, sms);
-        PVD_LAUNCH_PDL(false, (cols_conv2_kernel<512, 16, 32>), dim3((unsigned)grid), dim3(512), smem, stream, ca);
-        PVD_CUDA_CHECK("cols_conv2_kernel");
-        return PVD_OK;
-    }
-#endif
     if (p->fastCols[axis]) {
         const FastCols* f = p->fastCols[axis];
         const size_t smem = ((size_t)f->N * 16 + 4 * f->N) * sizeof(float2);
-        if (mode == COL_CONV) {
-            // experiment knob, off by default: L2-prefetching the spectrum lines and the tile of block id + pf_dist
-            // measured SLOWER on the B200 (P3 0.272 ms off, 0.290 / 0.309 / 0.318 / 0.336 ms for 2 / 148 / 296 / 592)
-            const char* e = getenv("PVD_PF_DIST");
-            a.pf_dist = e ? atoi(e) : 0;
-        }
-        static const int loop_knob = [] { const char* e = getenv("PVD_P3_LOOP"); return e ? atoi(e) : 1; }();
-        if (mode == COL_CONV && loop_knob && p->fnGrid[axis] > 0) {
-            // persistent walk over the tiles with the CTAs that are resident anyway (see cols_fast_kernel)
+        if (mode == COL_CONV && p->fnGrid[axis] > 0) {
+            // persistent walk over the tiles with the CTAs that are resident anyway (see cols_fast_kernel); launched
+            // normally: as a programmatic dependent this pass measured +70 us per C3 volume
             a.loop_ntz = (p->Nh + 15) / 16;
             a.loop_ntiles = a.loop_ntz * nouter;
-            a.pf_dist = 0;
-            static const int loop_pf = [] { const char* e = getenv("PVD_P3_PF"); return e ? atoi(e) : 0; }();
-            a.loop_pf = loop_pf;
             const int grid = std::min(a.loop_ntiles, p->fnGrid[axis]);
-            static const int p3_pdl = [] { const char* e = getenv("PVD_P3_PDL"); return e ? atoi(e) : 0; }();
-            PVD_LAUNCH_PDL(p->pdl && p3_pdl, f->fn[mode], dim3((unsigned)grid), dim3(f->fnNT[mode]), smem, stream, a);
+            PVD_LAUNCH_PDL(false, f->fn[mode], dim3((unsigned)grid), dim3(f->fnNT[mode]), smem, stream, a);
             PVD_CUDA_CHECK("cols_fast_kernel (looped)");
             return PVD_OK;
         }
@@ -518,17 +478,12 @@ int plan_finish(pvd_plan* p) {
     off = align_up(off + 256, 256);
     p->ws_bytes = off;
     p->algo = PVD_ALGO_FFT;
-    const char* force = getenv("PVD_FORCE_GENERIC");
-    if (!(force && force[0] == '1')) {
+    if (!force_generic()) {
         for (int a = 0; a < 2; ++a) p->fastCols[a] = find_fast_cols(p->m[a]);
         p->fastRows = find_fast_rows(p->m[2]);
         // the specialised column kernels index the work buffer with 32-bit element offsets
         if ((double)p->m[0] * p->m[1] * p->Sz >= 2147483648.0) p->fastCols[0] = p->fastCols[1] = nullptr;
     }
-    const char* nopipe = getenv("PVD_NO_PIPE");
-    p->usePipe = !(nopipe && nopipe[0] == '1');
-    const char* nopdl = getenv("PVD_PDL");
-    p->pdl = !(nopdl && nopdl[0] == '0');
     // ---- direct tiled convolution (TMA halo tiles): 'same'-type geometry, small kernels only
     bool direct_ok = (p->k[2] == 3 || p->k[2] == 5 || p->k[2] == 7) && p->k[0] <= 9 && p->k[1] <= 9 && p->n[2] % 4 == 0;
     for (int i = 0; i < 3; ++i) direct_ok = direct_ok && p->on[i] == p->n[i] && p->olo[i] == p->k[i] / 2;
@@ -556,29 +511,7 @@ void make_col_tensor_maps(pvd_plan* p) {
     p->tmaCols = false;
     p->tmaRows = false;
 #ifndef PVD_EMULATE
-    {
-        const char* er = getenv("PVD_TMA_ROWS");
-        p->tmaRows = !(er && er[0] == '0') && get_encode_tiled() != nullptr;
-    }
-    p->conv2 = false;
-    {
-        const char* ec = getenv("PVD_P3_DUAL");
-        if (ec && ec[0] == '1' && p->m[0] == 512 && get_encode_tiled()) {
-            memset(&p->tmapSpec, 0, sizeof(CUtensorMap));
-            const cuuint64_t gdim[3] = {(cuuint64_t)2 * p->Sz, (cuuint64_t)p->m[1], (cuuint64_t)p->m[0]};
-            const cuuint64_t gstr[2] = {(cuuint64_t)p->Sz * 8, (cuuint64_t)p->m[1] * p->Sz * 8};
-            const cuuint32_t box[3] = {32, 1, (cuuint32_t)tma_box_rows(512)};
-            const cuuint32_t estr[3] = {1, 1, 1};
-            const size_t smem = (size_t)3 * 512 * 16 * sizeof(float2) + 2 * 512 * sizeof(float2) + 64;
-            if (get_encode_tiled()(&p->tmapSpec, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->spec(), gdim, gstr, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
-                cudaFuncSetAttribute(cols_conv2_kernel<512, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
-                p->conv2 = true;
-        }
-    }
-    const char* e = getenv("PVD_TMA");
-    if (e && e[0] == '0') return;  // PVD_TMA=0: 16-byte cp.async staging instead (y passes at 512: 0.156 -> 0.150 ms with TMA)
+    p->tmaRows = get_encode_tiled() != nullptr;
     const FastCols* f = p->fastCols[1];
     EncodeTiledFn enc = get_encode_tiled();
     if (!f || !f->pipe[COL_FWD] || !enc) return;
@@ -676,9 +609,11 @@ int pvd_good_fft_size_axis(int n, int axis) { return good_size_axis(n, axis == 2
 int pvd_plan_create_ex(pvd_plan** out, const int n[3], const int m[3], const int out_lo[3], const int out_n[3],
                        const int k[3], int algo) {
     if (!out || !n || !out_lo || !out_n || !k) return fail(PVD_ERR_INVALID, "null argument");
-    if (algo != PVD_ALGO_AUTO && algo != PVD_ALGO_FFT && algo != PVD_ALGO_DIRECT) return fail(PVD_ERR_INVALID, "unknown algo %d", algo);
+    if (algo != PVD_ALGO_AUTO && algo != PVD_ALGO_FFT && algo != PVD_ALGO_DIRECT && algo != PVD_ALGO_FFT_UNPIPELINED)
+        return fail(PVD_ERR_INVALID, "unknown algo %d", algo);
     pvd_plan* p = new pvd_plan();
-    p->want_algo = algo;
+    p->want_algo = algo == PVD_ALGO_FFT_UNPIPELINED ? PVD_ALGO_FFT : algo;
+    p->usePipe = algo != PVD_ALGO_FFT_UNPIPELINED;
     for (int i = 0; i < 3; ++i) {
         p->n[i] = n[i];
         p->k[i] = k[i];
@@ -915,10 +850,6 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     a.Llog = p->rowLlog;
     a.tw = p->tw(2);
     a.st = p->st[2];
-    {
-        const char* e = getenv("PVD_DEN_PF");  // experiment knob
-        a.den_pf = e ? atoi(e) : 1;
-    }
     a.dense = (a.x_lo == 0 && a.y_lo == 0 && a.in_s0 == (long long)a.O1 * a.in_s1 && a.out_s0 == (long long)a.O1 * a.out_s1 &&
                a.den_s0 == (long long)a.O1 * a.den_s1)
                   ? 1
@@ -969,10 +900,6 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
                     a.use_tma_den = 1;
             }
-        }
-        {
-            static const int den_tma_knob = [] { const char* e = getenv("PVD_TMA_DEN"); return e ? atoi(e) : 1; }();
-            if (!den_tma_knob) a.use_tma_den = 0;
         }
 #endif
         PVD_LAUNCH_PDL(p->pdl, f->invPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
@@ -1031,9 +958,13 @@ int pvd_plan_check_device_errors(pvd_plan* p, void* stream_) {
         PVD_CUDA_CHECK("device error flags");
         return fail(PVD_ERR_CUDA, "device error flags: stream synchronise failed");
     }
-    if (p->algo == PVD_ALGO_DIRECT && flags[0] != 0)
-        return fail(PVD_ERR_CUDA, "direct convolution: a TMA tile load never completed (flag %d)", flags[0]);
-    if (flags[1] != 0) return fail(PVD_ERR_CUDA, "column pass: a TMA tile load never completed (flag %d)", flags[1]);
+    const bool bad0 = p->algo == PVD_ALGO_DIRECT && flags[0] != 0, bad1 = flags[1] != 0;
+    if (bad0 || bad1) {  // report once: the flag is sticky on the device, clear it so that the next execute starts clean
+        cudaMemsetAsync(p->flag(), 0, sizeof flags, stream);
+        cudaStreamSynchronize(stream);
+        if (bad0) return fail(PVD_ERR_CUDA, "direct convolution: a TMA tile load never completed (flag %d); the dose map of that execute is invalid", flags[0]);
+        return fail(PVD_ERR_CUDA, "FFT pass: a TMA tile load never completed (flag %d); the dose map of that execute is invalid", flags[1]);
+    }
     return PVD_OK;
 }
 

@@ -46,12 +46,12 @@ def _ptr(a: np.ndarray) -> int:
 class EmuConv:
     """NumPy-memory twin of pyvoxeldosimetry_b200.engine.ConvPlan for the emulated library."""
 
-    def __init__(self, lib, n, k, boundary=0, ex=None):
+    def __init__(self, lib, n, k, boundary=0, ex=None, algo=0):
         self.lib = lib
         if ex is None:
-            self.plan = lib.plan_create(n, k, boundary)
+            self.plan = lib.plan_create(n, k, boundary, algo)
         else:
-            self.plan = lib.plan_create_ex(n, ex["m"], ex["out_lo"], ex["out_n"], k)
+            self.plan = lib.plan_create_ex(n, ex["m"], ex["out_lo"], ex["out_n"], k, algo)
         self.info = lib.plan_info(self.plan)
         nbytes = lib.plan_workspace_bytes(self.plan)
         raw = np.zeros(nbytes + 256, dtype=np.uint8)

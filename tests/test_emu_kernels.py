@@ -200,7 +200,6 @@ FAST_CASES = [
 def test_fast_and_pipelined_kernels(lib, monkeypatch, shape, kshape, boundary, T, den, variant):
     if variant == "generic" and shape[0] * shape[1] * shape[2] > 40000:
         pytest.skip("generic engine already covered on small shapes")
-    monkeypatch.setenv("PVD_NO_PIPE", "1" if variant == "nopipe" else "0")
     monkeypatch.setenv("PVD_FORCE_GENERIC", "1" if variant == "generic" else "0")
     rng = np.random.default_rng(abs(hash((shape, kshape, boundary))) % 2**32)
     maps = [rng.uniform(0, 1e3, shape) for _ in range(T)]
@@ -208,7 +207,7 @@ def test_fast_and_pipelined_kernels(lib, monkeypatch, shape, kshape, boundary, T
     w = [0.25, 0.75][:T] if T > 1 else None
     k = rng.uniform(0, 1, kshape)
     rho = rng.uniform(0.2, 2.0, shape) if den else None
-    p = EmuConv(lib, shape, kshape, boundary)
+    p = EmuConv(lib, shape, kshape, boundary, algo=3 if variant == "nopipe" else 0)  # 3 = PVD_ALGO_FFT_UNPIPELINED
     p.set_kernel(k)
     got = p.execute(maps, w, rho)
     p.close()

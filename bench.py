@@ -248,45 +248,95 @@ def reference_step(maps64, kernel64, rho):
     return d
 
 
+def load_reference_calculator(wl):
+    """The reference's OWN class (core/kernel_convolution.py:26-76) from oracle/_ref (a byte-identical copy of
+    /root/reference made by oracle/ref_loader.py; it travels to the GPU box), with the workload's dose voxel kernel
+    produced by the reference's own generator and assigned through the public mutable attribute `calc.kernel`
+    (the class hard-codes a 64^3 grid, kernel_convolution.py:45).  The one NaN the Y90 / Ga68 generators leave at r = 0
+    (y90_kernel.py:134-138) is replaced by the finite centre value, as in SURVEY.md Appendix C.4 - with it every dose
+    voxel of the reference is NaN.  Returns (calculator, float64 kernel) or raises when oracle/_ref is absent."""
+    from oracle import dose_oracle as orc
+    from oracle import ref_loader
+
+    ref_loader.import_reference()
+    from pyvoxeldosimetry.core.kernel_convolution import KernelConvolutionCalculator as RefCalc
+    from pyvoxeldosimetry.data.dose_kernels.kernel_factory import KernelFactory as RefFactory
+
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        k = RefFactory().get_kernel(wl["nuclide"], "water", voxel_size=wl["voxel"], grid_size=tuple(wl["kgrid"]), force_regenerate=True)
+        calc = RefCalc(wl["nuclide"], "water", kernel_resolution=wl["voxel"])
+    k = np.array(k, dtype=np.float64)
+    bad = ~np.isfinite(k)
+    if bad.any():
+        k[bad] = orc.make_kernel(wl["nuclide"], wl["voxel"], wl["kgrid"])[bad]
+    calc.kernel = k
+    return calc, k
+
+
+def reference_step_real(calc, maps64, times, vox, rho):
+    """One unit of the reference's work through its own public API: T = 1 -> calculate_dose_rate, T > 1 ->
+    calculate_absorbed_dose (core/kernel_convolution.py:48-106); the density correction (absent from the reference,
+    core/dose_calculator.py:90) is the float64 NumPy formula of SURVEY section 8 A9 applied to its result."""
+    from oracle import dose_oracle as orc
+
+    if len(maps64) == 1:
+        d = calc.calculate_dose_rate(activity_map=maps64[0], voxel_size=vox)
+    else:
+        d = calc.calculate_absorbed_dose(activity_maps=maps64, time_points=times, voxel_size=vox)
+    if rho is not None:
+        d = orc.density_correct(d, rho)
+    return d
+
+
 def run_reference(args, wl):
+    """`--impl reference`: the UNMODIFIED reference class on the full workload shape, on this box's host cores
+    (np.fft is single-threaded by construction: cores = 1).  Every step is one full volume: K steps + W warm-ups of
+    ~10 s each for C3.  Falls back to the oracle port (kind "port") only when oracle/_ref was not built."""
     rank, world, local = dist_env()
     if rank != 0:
         return
     from oracle import dose_oracle as orc
 
     acts, times, rho = synth_inputs(wl)
-    k64 = orc.make_kernel(wl["nuclide"], wl["voxel"], wl["kgrid"]).astype(np.float32).astype(np.float64)
     nvox = float(np.prod(wl["shape"]))
-    total_budget = 150.0
-    per = total_budget / max(1, args.steps + args.warmup)
-    rate, sample, dt = cpu_reference_time(wl, per, acts, rho, k64)  # also serves as warm-up / calibration
-    pick = tuple(int(x) for x in sample.split(" on a ")[1].split(" ")[0].split("x"))
-    subs = [np.ascontiguousarray(m[: pick[0], : pick[1], : pick[2]]).astype(np.float64) for m in acts]
-    a = subs[0]
-    r = None if rho is None else rho[: pick[0], : pick[1], : pick[2]]
-    for _ in range(max(0, args.warmup - 1)):
-        reference_step(subs, k64, r)
+    maps64 = [a.astype(np.float64) for a in acts]
+    vox = (float(wl["voxel"]),) * 3
+    del acts
+    try:
+        calc, k64 = load_reference_calculator(wl)
+        kind = "reference"
+        what = ("pyvoxeldosimetry.core.kernel_convolution.KernelConvolutionCalculator." +
+                ("calculate_dose_rate" if wl["T"] == 1 else "calculate_absorbed_dose") + " of oracle/_ref (byte-identical copy of the reference)")
+        step = lambda: reference_step_real(calc, maps64, times, vox, rho)
+    except Exception as e:  # oracle/_ref not built (no /root/reference at build time): literal port of the same four lines
+        sys.stderr.write(f"[bench] reference package unavailable ({e}); timing the oracle port\n")
+        k64 = orc.make_kernel(wl["nuclide"], wl["voxel"], wl["kgrid"]).astype(np.float32).astype(np.float64)
+        kind, what = "port", "oracle.conv_reference (literal np.fft expression of core/kernel_convolution.py:71-74)"
+        step = lambda: reference_step(maps64, k64, rho)
+    for _ in range(args.warmup):
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        reference_step(subs, k64, r)
-    dt = (time.perf_counter() - t0) / args.steps
-    vps = a.size / dt
-    value = vps / nvox
+        d = step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = 1.0 / dt
+    sample = (f"{what}, float64, full {wl['shape'][0]}x{wl['shape'][1]}x{wl['shape'][2]} volume per step, {args.steps} steps after "
+              f"{args.warmup} warm-ups; np.fft is single-threaded" + ("; + float64 NumPy density correction" if rho is not None else ""))
     line = {
-        "impl": "reference", "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": vps,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * nvox / a.size,
+        "impl": "reference", "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "boundary": args.boundary, "note": "volumes/s = measured voxels/s on the sample / voxels per volume"},
-        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": 1, "kind": "port", "sample": sample + f", {args.steps} steps; np.fft is single-threaded"},
+        "config": {"workload": wl["desc"], "boundary": args.boundary, "volumes_per_step_per_gpu": 1,
+                   "l2": "inputs (>=419 MB per volume for c3) exceed the 126 MB L2",
+                   "parallelism": "one host process, one thread (the reference has no parallelism)"},
+        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count(), "finite": bool(np.isfinite(d).all())},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    try:
-        tv, tc = cpu_threaded_time(wl, acts, rho, k64, pick)
-        line["cpu_threaded"] = {"value": tv, "unit": "volumes/s", "cores": tc, "kind": "port",
-                                "what": "same mathematics, scipy.fft rfftn/irfftn with workers = all host threads (not the reference's own code path), same sample"}
-    except Exception as e:  # pragma: no cover - scipy missing / signature drift: the literal figure stands
-        line["cpu_threaded"] = {"unavailable": str(e)[:200]}
     emit(line)
 
 

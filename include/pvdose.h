@@ -154,6 +154,29 @@ int pvd_kernel_eval_radial(const pvd_radial_model* model, const double spacing_m
 int pvd_hu_to_density_f32(const float* hu, const float* h_knots, int nk, float* rho, size_t n, void* stream);
 int pvd_hu_to_density_i16(const int16_t* hu, const float* h_knots, int nk, float* rho, size_t n, void* stream);
 
+/* ---- Host-buffer staging: the reference's calling convention is pageable host NumPy arrays in, a host array out
+ * (core/kernel_convolution.py:48-76; the examples pass float64 np.zeros volumes).  A stager owns a ring of pinned chunks
+ * and a pool of host threads (csrc/host_stage.cuh).  `h_` pointers are HOST memory (pageable or pinned).
+ *  - pvd_stage_h2d: n elements of `dtype` from h_src to d_dst on `stream`.  PVD_DTYPE_F64 is narrowed to float32 by the
+ *    host threads (half the bytes over the link); F32 / I16 / U16 arrive as they are.  Returns when h_src has been read
+ *    completely (the caller may reuse it) and every chunk copy is enqueued on `stream`.
+ *  - pvd_stage_d2h: n float32 from d_src (after the work already enqueued on `stream`) to h_dst as float32 or float64
+ *    (the reference returns float64); returns when h_dst is complete.
+ * threads / chunk_bytes / ring_chunks = 0 pick the defaults (min(8, usable CPUs), 4 MiB, 2 * threads + 2). ---- */
+#define PVD_DTYPE_F32 0
+#define PVD_DTYPE_F64 1
+#define PVD_DTYPE_I16 2
+#define PVD_DTYPE_U16 3
+typedef struct pvd_stager pvd_stager;
+int pvd_stager_create(pvd_stager** out, int threads, size_t chunk_bytes, int ring_chunks);
+int pvd_stager_destroy(pvd_stager* s);
+int pvd_stage_h2d(pvd_stager* s, const void* h_src, int dtype, void* d_dst, size_t n, void* stream);
+int pvd_stage_d2h(pvd_stager* s, const float* d_src, void* h_dst, int dtype, size_t n, void* stream);
+
+/* 16-bit stored activity (the PET DICOM pixel data the reference reads and rescales on the host, io/dicom.py:27-47)
+ * -> float32 activity on the device: out = slope * stored + intercept.  The volume crosses the link at 2 bytes/voxel. */
+int pvd_i16_to_f32(const void* d_in, int is_unsigned, float slope, float intercept, float* d_out, size_t n, void* stream);
+
 /* ---- A3: ActivitySampler._trapezoid_integration (core/activity_sampler.py:69-79) and the missing
  * integrate_dose_rates (core/dose_calculator.py:138): out = sum_t h_weights[t] * vol[t]. T <= 16. ---- */
 int pvd_weighted_sum(const float* const* h_vol, const float* h_weights, int T, float* out, size_t n, void* stream);

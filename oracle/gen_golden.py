@@ -33,46 +33,14 @@ REF = "/root/reference"
 OUT = os.path.join(REPO, "tests", "golden")
 
 
-class _Stub(types.ModuleType):
-    """Permissive stand-in for an absent third-party module."""
-
-    def __getattr__(self, name):
-        if name.startswith("__") and name.endswith("__"):
-            raise AttributeError(name)
-        child = _Stub(f"{self.__name__}.{name}")
-        setattr(self, name, child)
-        return child
-
-    def __call__(self, *a, **k):
-        # decorators such as @cp.fuse() must hand back a callable that returns its argument
-        if len(a) == 1 and callable(a[0]) and not k:
-            return a[0]
-        return self
-
-
 def import_reference():
-    tmp = tempfile.mkdtemp(prefix="pvd_ref_")
-    shutil.copytree(os.path.join(REF, "pyvoxeldosimetry"), os.path.join(tmp, "pyvoxeldosimetry"))
-    for name in [
-        "nibabel", "nibabel.processing", "SimpleITK", "pydicom", "pydicom.dataset", "pydicom.uid",
-        "cupy", "matplotlib", "matplotlib.pyplot",
-    ]:
-        sys.modules[name] = _Stub(name)
-    # make sure our own drop-in alias package does not shadow the reference
-    sys.path = [p for p in sys.path if os.path.abspath(p or ".") != REPO]
-    for k in [k for k in sys.modules if k == "pyvoxeldosimetry" or k.startswith("pyvoxeldosimetry.")]:
-        del sys.modules[k]
-    sys.path.insert(0, tmp)
-    import pyvoxeldosimetry  # noqa: F401
-    from pyvoxeldosimetry.data.dose_kernels import base_kernel
+    """The real reference, copied to oracle/_ref and imported under the stub recipe (oracle/ref_loader.py)."""
+    sys.path.insert(0, REPO)
+    from oracle import ref_loader
 
-    def _load_config(self, config_path):
-        with open(config_path, "r") as f:
-            return json.loads(re.sub(r"//[^\n]*", "", f.read()))
-
-    base_kernel.BaseKernelGenerator._load_config = _load_config
-    base_kernel.BaseKernelGenerator.save_kernel = lambda self, kernel, output_dir: None  # no png/npy side effects
-    return tmp
+    ref_loader.build_ref()
+    ref_loader.import_reference()
+    return None
 
 
 def gen_next_rows(orc):
@@ -268,7 +236,6 @@ def main():
     gen_next_rows(orc)
     with open(os.path.join(OUT, "kats.json"), "w") as f:
         json.dump({k: float(v) for k, v in kats.items()}, f, indent=1, sort_keys=True)
-    shutil.rmtree(tmp, ignore_errors=True)
     print("golden written to", OUT)
     for fn in sorted(os.listdir(OUT)):
         print(f"  {fn}: {os.path.getsize(os.path.join(OUT, fn))} bytes")

@@ -25,7 +25,9 @@ SYMBOLS = [
     "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
     "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
     "pvd_density_scale", "pvd_monoexp_fit", "pvd_ct_prepare", "pvd_roi_minmax", "pvd_dvh_histogram",
+    "pvd_stager_create", "pvd_stager_destroy", "pvd_stage_h2d", "pvd_stage_d2h", "pvd_i16_to_f32",
 ]
+DTYPE_F32, DTYPE_F64, DTYPE_I16, DTYPE_U16 = 0, 1, 2, 3
 
 
 class PvdoseLibraryError(RuntimeError):
@@ -96,6 +98,11 @@ class PvdLib:
         d.pvd_ct_prepare.argtypes = [vp, ip, C.c_float, fp, C.c_int, fp, C.c_int, vp, vp, vp, vp]
         d.pvd_roi_minmax.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, fp, fp, C.POINTER(C.c_ulonglong), vp]
         d.pvd_dvh_histogram.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, C.c_int, C.c_float, C.c_float, vp, vp]
+        d.pvd_stager_create.argtypes = [C.POINTER(vp), C.c_int, C.c_size_t, C.c_int]
+        d.pvd_stager_destroy.argtypes = [vp]
+        d.pvd_stage_h2d.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, vp]
+        d.pvd_stage_d2h.argtypes = [vp, vp, vp, C.c_int, C.c_size_t, vp]
+        d.pvd_i16_to_f32.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp, C.c_size_t, vp]
 
     # ------------------------------------------------------------------ helpers
     def check(self, rc: int):
@@ -219,6 +226,25 @@ class PvdLib:
     def dvh_histogram(self, dose_ptr: int, mask_ptr: int, mask_is_f32: bool, n: int, edges_ptr: int, bins: int, first: float,
                       last: float, hist_ptr: int, stream: int = 0):
         self.check(self.dll.pvd_dvh_histogram(dose_ptr, mask_ptr, 1 if mask_is_f32 else 0, n, edges_ptr, bins, first, last, hist_ptr, stream))
+
+
+    # ------------------------------------------------------------------ host-buffer staging
+    def stager_create(self, threads: int = 0, chunk_bytes: int = 0, ring_chunks: int = 0) -> int:
+        h = C.c_void_p()
+        self.check(self.dll.pvd_stager_create(C.byref(h), threads, chunk_bytes, ring_chunks))
+        return h.value
+
+    def stager_destroy(self, stager: int):
+        self.dll.pvd_stager_destroy(stager)
+
+    def stage_h2d(self, stager: int, host_ptr: int, dtype: int, dev_ptr: int, n: int, stream: int = 0):
+        self.check(self.dll.pvd_stage_h2d(stager, host_ptr, dtype, dev_ptr, n, stream))
+
+    def stage_d2h(self, stager: int, dev_ptr: int, host_ptr: int, dtype: int, n: int, stream: int = 0):
+        self.check(self.dll.pvd_stage_d2h(stager, dev_ptr, host_ptr, dtype, n, stream))
+
+    def i16_to_f32(self, in_ptr: int, is_unsigned: bool, slope: float, intercept: float, out_ptr: int, n: int, stream: int = 0):
+        self.check(self.dll.pvd_i16_to_f32(in_ptr, 1 if is_unsigned else 0, slope, intercept, out_ptr, n, stream))
 
 
 _LIB: Optional[PvdLib] = None

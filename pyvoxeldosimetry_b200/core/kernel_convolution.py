@@ -123,18 +123,48 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         so an int16 CT crosses the PCIe link at 2 bytes per voxel."""
         from ..tissue.density import HU_KNOTS
 
+        if tuple(ct_hu.shape) != tuple(shape):
+            raise ValueError("ct_hu must have the shape of the activity map")
         if isinstance(ct_hu, torch.Tensor):
             t = ct_hu if ct_hu.dtype in (torch.int16, torch.float32) else ct_hu.to(torch.float32)
+            t = t.to(self.device, non_blocking=True).contiguous()
         else:
             a = np.ascontiguousarray(ct_hu)
-            t = torch.from_numpy(a if a.dtype in (np.int16, np.float32) else a.astype(np.float32))
-        if tuple(t.shape) != tuple(shape):
-            raise ValueError("ct_hu must have the shape of the activity map")
-        t = t.to(self.device, non_blocking=True).contiguous()
+            if a.dtype not in (np.int16, np.float32, np.float64):
+                a = a.astype(np.float32)
+            if engine._stageable(a):
+                t = engine.HostStager.get(self.device).upload(a)  # int16 stays int16 (2 bytes per voxel over the link)
+            else:
+                t = torch.from_numpy(a if a.dtype != np.float64 else a.astype(np.float32)).to(self.device, non_blocking=True)
         return engine.hu_to_density(t, self.config.get("hu_knots", HU_KNOTS))
 
+    def _activity_to_device(self, m, rescale=None) -> torch.Tensor:
+        """Activity volume -> float32 device tensor.  16-bit stored activity (the PET DICOM pixel data the reference
+        rescales on the host, io/dicom.py:27-47) crosses the link at 2 bytes per voxel and becomes
+        slope * stored + intercept on the device; `rescale` = (slope, intercept), default (1, 0)."""
+        is16 = (isinstance(m, np.ndarray) and m.dtype in (np.int16, np.uint16)) or \
+               (isinstance(m, torch.Tensor) and m.dtype in (torch.int16, torch.uint16))
+        if not is16:
+            if rescale is not None:
+                raise ValueError("rescale=(slope, intercept) applies to int16 / uint16 stored activity only")
+            return engine.to_device_f32(m, self.device)
+        slope, intercept = (1.0, 0.0) if rescale is None else (float(rescale[0]), float(rescale[1]))
+        if isinstance(m, torch.Tensor):
+            unsigned = m.dtype == torch.uint16
+            raw = m.view(torch.int16).to(self.device, non_blocking=True).contiguous()
+        else:
+            unsigned = m.dtype == np.uint16
+            a = np.ascontiguousarray(m)
+            raw = engine.HostStager.get(self.device).upload(a) if engine._stageable(a) else \
+                torch.from_numpy(a.view(np.int16)).to(self.device, non_blocking=True)
+        out = torch.empty(raw.shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            engine.get_lib().i16_to_f32(raw.data_ptr(), unsigned, slope, intercept, out.data_ptr(), raw.numel(),
+                                        torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
     def _convolve(self, maps: Sequence, weights: Optional[Sequence[float]], voxel_size, tissue_densities=None,
-                  out: Optional[np.ndarray] = None, ct_hu=None):
+                  out: Optional[np.ndarray] = None, ct_hu=None, rescale=None):
         if len(maps) == 0:
             raise ValueError("No activity maps provided")
         shape = tuple(maps[0].shape)
@@ -145,7 +175,7 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         kdev, tag = self._kernel_for(voxel_size)
         plan = self._plans.get(shape, tuple(kdev.shape), self.boundary, self.device, tag, lambda: kdev, self.algo)
         self._last_plan = plan
-        acts = [engine.to_device_f32(m, self.device) for m in maps]
+        acts = [self._activity_to_device(m, rescale) for m in maps]
         den = None
         if tissue_densities is not None and ct_hu is not None:
             raise ValueError("give tissue_densities or ct_hu, not both")
@@ -162,14 +192,9 @@ class KernelConvolutionCalculator(DosimetryCalculator):
 
     def _to_host(self, dose: torch.Tensor, out=None) -> np.ndarray:
         want64 = str(self.config.get("output_dtype", "float32")) == "float64"
-        if out is not None:
-            tgt = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
-            tgt.copy_(dose, non_blocking=False)
-            self._check_device_errors()
-            return out if not isinstance(out, torch.Tensor) else out.numpy()
-        host = dose.cpu().numpy()
+        host = engine.to_host(dose, out, want64)
         self._check_device_errors()
-        return host.astype(np.float64) if want64 else host
+        return out if (out is not None and not isinstance(out, torch.Tensor)) else host
 
     def _check_device_errors(self) -> None:
         """Every host-returning path ends here: read (and clear) the device-side TMA watchdog flags of the plans this
@@ -181,16 +206,17 @@ class KernelConvolutionCalculator(DosimetryCalculator):
 
     # ------------------------------------------------------------------ reference API
     def calculate_dose_rate(self, activity_map, voxel_size: Tuple[float, float, float] = None,
-                            tissue_densities=None, out=None, ct_hu=None):
+                            tissue_densities=None, out=None, ct_hu=None, rescale=None):
         """A1.  Host ndarray in -> host ndarray out; CUDA tensor in -> CUDA tensor out (no copies).
-        Density correction (A9): `tissue_densities` (g/cm3) or `ct_hu` (the CT in Hounsfield units, int16 or float)."""
-        dose = self._convolve([activity_map], None, voxel_size, tissue_densities, ct_hu=ct_hu)
+        Density correction (A9): `tissue_densities` (g/cm3) or `ct_hu` (the CT in Hounsfield units, int16 or float).
+        `activity_map` may be float64 / float32, or int16 / uint16 stored values with `rescale` = (slope, intercept)."""
+        dose = self._convolve([activity_map], None, voxel_size, tissue_densities, ct_hu=ct_hu, rescale=rescale)
         if isinstance(activity_map, torch.Tensor) and activity_map.is_cuda:
             return dose
         return self._to_host(dose, out)
 
     def calculate_dose_rate_batch(self, activity_maps: Sequence, voxel_size=None, tissue_densities=None,
-                                  outs: Optional[Sequence] = None, ct_hu=None) -> list:
+                                  outs: Optional[Sequence] = None, ct_hu=None, rescale=None) -> list:
         """A1 for a batch of independent host volumes (one per patient / time point), software pipelined:
         the H2D copy of volume i+1, the convolution of volume i and the D2H copy of volume i-1 run on three
         CUDA streams with double-buffered device tensors, so the PCIe link (the end-to-end bottleneck: the
@@ -198,7 +224,8 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         volume shared by all, or one per activity map.  `outs`: optional host tensors/arrays to fill (pinned
         host tensors avoid a staging copy; they may repeat, e.g. two alternating buffers).  `ct_hu`: instead of
         densities, one int16 CT volume (Hounsfield units) per activity map (or one shared); it is copied as int16
-        (2 bytes per voxel over the link) and turned into density on the device."""
+        (2 bytes per voxel over the link) and turned into density on the device.  int16 / uint16 activity volumes
+        (stored PET values) are copied as 16-bit and become slope * stored + intercept on the device (`rescale`)."""
         n = len(activity_maps)
         if ct_hu is not None:
             if tissue_densities is not None:
@@ -241,6 +268,17 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         for s in (s_in, s_cmp, s_out):
             s.wait_event(start)
         d_act = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        first = activity_maps[0]
+        act16 = (first.dtype in (torch.int16, torch.uint16)) if isinstance(first, torch.Tensor) else (np.asarray(first).dtype in (np.int16, np.uint16))
+        act_unsigned = act16 and ((first.dtype == torch.uint16) if isinstance(first, torch.Tensor) else (np.asarray(first).dtype == np.uint16))
+        slope, intercept = (1.0, 0.0) if rescale is None else (float(rescale[0]), float(rescale[1]))
+        if rescale is not None and not act16:
+            raise ValueError("rescale=(slope, intercept) applies to int16 / uint16 stored activity only")
+        d_raw = [torch.empty(shape, dtype=torch.int16, device=dev) for _ in range(2)] if act16 else None
+
+        def host_raw16(x):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x).view(np.int16))
+            return t.view(torch.int16)
         d_out = [torch.empty(plan.out_shape, dtype=torch.float32, device=dev) for _ in range(2)]
         d_den = None
         if tissue_densities is not None:
@@ -262,7 +300,10 @@ class KernelConvolutionCalculator(DosimetryCalculator):
             with torch.cuda.stream(s_in):
                 if i >= 2:
                     s_in.wait_event(ev_cmp[i - 2])  # device input slot free again
-                d_act[slot].copy_(host_f32(activity_maps[i]), non_blocking=True)
+                if act16:
+                    d_raw[slot].copy_(host_raw16(activity_maps[i]), non_blocking=True)
+                else:
+                    d_act[slot].copy_(host_f32(activity_maps[i]), non_blocking=True)
                 if d_den is not None and per_vol_ct:
                     h = host_i16(tissue_densities[i])
                     if tuple(h.shape) != plan.out_shape:
@@ -276,6 +317,10 @@ class KernelConvolutionCalculator(DosimetryCalculator):
                 if i >= 2:
                     s_cmp.wait_event(ev_out[i - 2])  # device output slot drained
                 den = None if tissue_densities is None else (d_den[slot] if d_den is not None else shared)
+                if act16:  # stored 16-bit activity -> float32 on the device (d_act[slot] is free: ev_cmp[i - 2] has been waited for)
+                    with torch.cuda.device(dev):
+                        engine.get_lib().i16_to_f32(d_raw[slot].data_ptr(), act_unsigned, slope, intercept, d_act[slot].data_ptr(),
+                                                    d_act[slot].numel(), torch.cuda.current_stream(dev).cuda_stream)
                 if per_vol_ct:  # HU -> density on the device, in the compute stream (d_den[slot] is free: see ev_out wait)
                     self._lib_hu_to_density(d_hu[slot], knots, d_den[slot])
                 plan.execute([d_act[slot]], None, den, rr, rm, rc, sc, out=d_out[slot])

@@ -67,6 +67,13 @@ __global__ void hu_to_density_kernel(const T* __restrict__ hu, const Knots k, fl
     }
 }
 
+// 16-bit stored activity (PET DICOM pixel data) -> float32: out = slope * stored + intercept (io/dicom.py:27-47)
+template <class T>
+__global__ void rescale_to_f32_kernel(const T* __restrict__ in, float slope, float intercept, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = fmaf(slope, (float)in[i], intercept);
+}
+
 struct WsumArgs {
     const float* v[kMaxT];
     float w[kMaxT];

@@ -13,6 +13,7 @@
 #include "fft_pipe.cuh"
 #include "fft_rows_pipe.cuh"
 #include "fft_passes.cuh"
+#include "host_stage.cuh"
 
 using namespace pvd;
 
@@ -176,7 +177,14 @@ struct FastRows {
 #define PVD_ROWS_NOPIPE(N, NT, R1, R2, R3) \
     { N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>, nullptr, nullptr, 0 }
 const FastCols kFastCols[] = {
+#ifdef PVD_EXP_Y1632  // experiment build: every 512-point column pass on the two-stage 16*32 register kernel (2 x 256 threads per SM, tile walk)
+    {512, 256,
+     {cols_fast_kernel<512, 256, 16, 32, 1, COL_FWD, 2>, cols_fast_kernel<512, 256, 16, 32, 1, COL_INV, 2>,
+      cols_fast_kernel<512, 256, 16, 32, 1, COL_CONV, 2>, cols_fast_kernel<512, 256, 16, 32, 1, COL_SPEC, 2>},
+     {nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}, {256, 256, 256, 256}},
+#else
     PVD_COLS_CX(512, 512, 1, 8, 8, 8, 256, 2, 16, 32, 1),
+#endif
     PVD_COLS(256, 256, 2, 16, 16, 1),
     PVD_COLS(400, 320, 1, 20, 20, 1),
     PVD_COLS(576, 384, 1, 24, 24, 1),   // 512 + kernel reach ('same' mode of 512-wide volumes)
@@ -414,7 +422,12 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
     if (p->fastCols[axis]) {
         const FastCols* f = p->fastCols[axis];
         const size_t smem = ((size_t)f->N * 16 + 4 * f->N) * sizeof(float2);
-        if (mode == COL_CONV && p->fnGrid[axis] > 0) {
+#ifdef PVD_EXP_Y1632
+        const bool walk = p->fnGrid[axis] > 0 && f->N == 512;
+#else
+        const bool walk = mode == COL_CONV && p->fnGrid[axis] > 0;
+#endif
+        if (walk) {
             // persistent walk over the tiles with the CTAs that are resident anyway (see cols_fast_kernel); launched
             // normally: as a programmatic dependent this pass measured +70 us per C3 volume
             a.loop_ntz = (p->Nh + 15) / 16;
@@ -1039,6 +1052,19 @@ int pvd_hu_to_density_i16(const int16_t* hu, const float* h_knots, int nk, float
     return PVD_OK;
 }
 
+int pvd_i16_to_f32(const void* d_in, int is_unsigned, float slope, float intercept, float* d_out, size_t n, void* stream) {
+    if (!d_in || !d_out) return fail(PVD_ERR_INVALID, "null argument");
+    if (n == 0) return PVD_OK;
+    if (is_unsigned)
+        PVD_LAUNCH(rescale_to_f32_kernel<unsigned short>, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream,
+                   (const unsigned short*)d_in, slope, intercept, d_out, n);
+    else
+        PVD_LAUNCH(rescale_to_f32_kernel<short>, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const short*)d_in, slope,
+                   intercept, d_out, n);
+    PVD_CUDA_CHECK("rescale_to_f32_kernel");
+    return PVD_OK;
+}
+
 int pvd_weighted_sum(const float* const* h_vol, const float* h_weights, int T, float* out, size_t n, void* stream) {
     if (!h_vol || !out) return fail(PVD_ERR_INVALID, "null argument");
     if (T < 1 || T > PVD_MAX_T) return fail(PVD_ERR_INVALID, "T=%d outside [1,%d]", T, PVD_MAX_T);
@@ -1221,5 +1247,87 @@ int pvd_dvh_histogram(const float* dose, const void* mask, int mask_is_f32, size
     PVD_CUDA_CHECK("dvh_hist_kernel");
     return PVD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer staging (host_stage.cuh)
+#ifdef PVD_EMULATE
+struct pvd_stager { int threads; };
+int pvd_stager_create(pvd_stager** out, int threads, size_t, int) {
+    if (!out) return fail(PVD_ERR_INVALID, "null argument");
+    *out = new pvd_stager{threads > 0 ? threads : 1};
+    return PVD_OK;
+}
+int pvd_stager_destroy(pvd_stager* s) {
+    delete s;
+    return PVD_OK;
+}
+int pvd_stage_h2d(pvd_stager* s, const void* h_src, int dt, void* d_dst, size_t n, void*) {
+    if (!s || !h_src || !d_dst) return fail(PVD_ERR_INVALID, "null argument");
+    if (dt == PVD_DTYPE_F64) {
+        for (size_t i = 0; i < n; ++i) ((float*)d_dst)[i] = (float)((const double*)h_src)[i];
+    } else {
+        memcpy(d_dst, h_src, n * (dt == PVD_DTYPE_F32 ? 4 : 2));
+    }
+    return PVD_OK;
+}
+int pvd_stage_d2h(pvd_stager* s, const float* d_src, void* h_dst, int dt, size_t n, void*) {
+    if (!s || !d_src || !h_dst) return fail(PVD_ERR_INVALID, "null argument");
+    if (dt == PVD_DTYPE_F64) {
+        for (size_t i = 0; i < n; ++i) ((double*)h_dst)[i] = (double)d_src[i];
+    } else if (dt == PVD_DTYPE_F32) {
+        memcpy(h_dst, d_src, n * 4);
+    } else {
+        return fail(PVD_ERR_INVALID, "dose maps leave as float32 or float64");
+    }
+    return PVD_OK;
+}
+#else
+struct pvd_stager {
+    pvd::Stager impl;
+    pvd_stager(int t, size_t c, int r) : impl(t, c, r) {}
+};
+int pvd_stager_create(pvd_stager** out, int threads, size_t chunk_bytes, int ring_chunks) {
+    if (!out) return fail(PVD_ERR_INVALID, "null argument");
+    if (threads <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        threads = (int)std::min(8u, hw ? hw : 4u);
+#ifdef __linux__
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) threads = std::max(1, std::min(threads, CPU_COUNT(&set)));
+#endif
+    }
+    if (chunk_bytes == 0) chunk_bytes = (size_t)4 << 20;
+    if (ring_chunks <= 0) ring_chunks = 2 * threads + 2;
+    if (threads > 64 || chunk_bytes < 4096 || chunk_bytes % 256 != 0 || ring_chunks < 2 || ring_chunks > 256)
+        return fail(PVD_ERR_INVALID, "stager: threads <= 64, chunk a multiple of 256 bytes >= 4096, 2..256 ring chunks");
+    pvd_stager* s = new pvd_stager(threads, chunk_bytes, ring_chunks);
+    const cudaError_t e = s->impl.init();
+    if (e != cudaSuccess) {
+        delete s;
+        cudaGetLastError();
+        return fail(PVD_ERR_CUDA, "stager: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return PVD_OK;
+}
+int pvd_stager_destroy(pvd_stager* s) {
+    delete s;
+    return PVD_OK;
+}
+int pvd_stage_h2d(pvd_stager* s, const void* h_src, int dt, void* d_dst, size_t n, void* stream) {
+    if (!s || !h_src || !d_dst) return fail(PVD_ERR_INVALID, "null argument");
+    if (dt < PVD_DTYPE_F32 || dt > PVD_DTYPE_U16) return fail(PVD_ERR_INVALID, "unknown host dtype %d", dt);
+    const cudaError_t e = s->impl.h2d(h_src, dt, d_dst, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(PVD_ERR_CUDA, "staged host-to-device copy: %s", cudaGetErrorString(e));
+    return PVD_OK;
+}
+int pvd_stage_d2h(pvd_stager* s, const float* d_src, void* h_dst, int dt, size_t n, void* stream) {
+    if (!s || !d_src || !h_dst) return fail(PVD_ERR_INVALID, "null argument");
+    if (dt != PVD_DTYPE_F32 && dt != PVD_DTYPE_F64) return fail(PVD_ERR_INVALID, "dose maps leave as float32 or float64");
+    const cudaError_t e = s->impl.d2h(d_src, h_dst, dt, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(PVD_ERR_CUDA, "staged device-to-host copy: %s", cudaGetErrorString(e));
+    return PVD_OK;
+}
+#endif
 
 }  // extern "C"

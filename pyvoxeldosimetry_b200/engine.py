@@ -33,16 +33,99 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_NP_STAGE_DTYPES = {np.dtype(np.float32): _capi.DTYPE_F32, np.dtype(np.float64): _capi.DTYPE_F64,
+                    np.dtype(np.int16): _capi.DTYPE_I16, np.dtype(np.uint16): _capi.DTYPE_U16}
+STAGE_MIN_BYTES = 1 << 20  # smaller host arrays take the plain torch copy
+
+
+class HostStager:
+    """Pinned-ring + host-thread staging between pageable host ndarrays and device tensors (pvd_stager_*,
+    csrc/host_stage.cuh).  One per device, created on first use."""
+
+    _per_device: Dict[str, "HostStager"] = {}
+    _lock = threading.Lock()
+
+    @classmethod
+    def get(cls, device: torch.device) -> "HostStager":
+        key = str(device)
+        with cls._lock:
+            st = cls._per_device.get(key)
+            if st is None:
+                st = cls._per_device[key] = HostStager(device)
+            return st
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.lib = get_lib()
+        with torch.cuda.device(device):
+            self.handle = self.lib.stager_create(0, 0, 0)
+
+    def upload(self, arr: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """C-contiguous float32 / float64 / int16 / uint16 ndarray -> device tensor (float64 narrowed to float32 on the
+        host; uint16 arrives in an int16 tensor, bit for bit).  Enqueued on the current stream; `arr` is free on return."""
+        code = _NP_STAGE_DTYPES[arr.dtype]
+        tdt = torch.float32 if code in (_capi.DTYPE_F32, _capi.DTYPE_F64) else torch.int16
+        if out is None:
+            out = torch.empty(arr.shape, dtype=tdt, device=self.device)
+        with torch.cuda.device(self.device):
+            self.lib.stage_h2d(self.handle, arr.ctypes.data, code, out.data_ptr(), arr.size, _stream_ptr(self.device))
+        return out
+
+    def download(self, dev: torch.Tensor, out: np.ndarray) -> np.ndarray:
+        """float32 device tensor -> C-contiguous float32 / float64 host ndarray (complete on return)."""
+        code = _NP_STAGE_DTYPES[out.dtype]
+        with torch.cuda.device(self.device):
+            self.lib.stage_d2h(self.handle, dev.data_ptr(), out.ctypes.data, code, dev.numel(), _stream_ptr(self.device))
+        return out
+
+
+def _stageable(a: np.ndarray) -> bool:
+    return a.dtype in _NP_STAGE_DTYPES and a.flags.c_contiguous and a.nbytes >= STAGE_MIN_BYTES
+
+
 def to_device_f32(x, device: torch.device) -> torch.Tensor:
-    """Host ndarray / tensor -> contiguous float32 CUDA tensor (no copy when already there)."""
+    """Host ndarray / tensor -> contiguous float32 CUDA tensor (no copy when already there).  Large float32 / float64
+    ndarrays go through the staging engine (host threads + pinned ring; float64 is narrowed on the host)."""
     if isinstance(x, torch.Tensor):
         t = x
     else:
         a = np.asarray(x)
+        if a.dtype in (np.float32, np.float64) and _stageable(a):
+            return HostStager.get(device).upload(a)
         if a.dtype != np.float32:
             a = a.astype(np.float32)
         t = torch.from_numpy(np.ascontiguousarray(a))
     return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def to_host(dev: torch.Tensor, out=None, want64: bool = False) -> np.ndarray:
+    """float32 device tensor -> host ndarray, complete on return.
+      out=None        the result lives in pinned memory from torch's caching host allocator (one straight D2H at link
+                      speed, no host copy); the ndarray owns the block, which returns to the cache when it is dropped;
+                      want64 -> a float64 ndarray filled by the staging threads (the reference returns float64);
+      out=ndarray     filled through the staging engine (float32 or float64, C-contiguous);
+      out=torch CPU tensor (pinned or not): plain copy."""
+    device = dev.device
+    if out is None:
+        if want64:
+            res = np.empty(tuple(dev.shape), dtype=np.float64)
+            if _stageable(res):
+                return HostStager.get(device).download(dev, res)
+            res[...] = dev.cpu().numpy()
+            return res
+        host = torch.empty(tuple(dev.shape), dtype=torch.float32, pin_memory=True)
+        host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        return host.numpy()
+    if isinstance(out, torch.Tensor):
+        out.copy_(dev, non_blocking=False)
+        return out.numpy()
+    if tuple(out.shape) != tuple(dev.shape):
+        raise ValueError("out has the wrong shape")
+    if _stageable(out) and out.dtype in (np.float32, np.float64):
+        return HostStager.get(device).download(dev, out)
+    out[...] = dev.cpu().numpy()
+    return out
 
 
 class ConvPlan:

@@ -68,6 +68,9 @@ typedef struct pvd_plan_info {
 } pvd_plan_info;
 
 int pvd_version(void);
+/* Hash of the CUDA sources this library was built from (stamped by __graft_entry__.build()); measured artefacts that depend
+ * on the kernels (ncu DRAM traffic) carry it so that stale ones can be told apart. */
+const char* pvd_build_id(void);
 const char* pvd_last_error(void);
 
 /* Smallest transform length >= n the engine handles efficiently ({2,3,5,7}-smooth, few radix stages). */
@@ -109,6 +112,18 @@ int pvd_plan_set_kernel(pvd_plan* plan, const float* kernel, void* stream);
 int pvd_conv_execute(pvd_plan* plan, const float* const* h_act, const float* h_weights, int T,
                      const float* density, float rho_ref, float rho_min, float rho_cut, float scale, float* dose,
                      void* stream);
+
+/* Split form of pvd_conv_execute for the z-slab decomposition (no reference counterpart - the
+ * reference is single-process).  The plane-local forward passes (z real-to-complex with the time-weighted sum, y forward)
+ * of input planes [plane_lo, plane_hi) are independent of every other plane, so a rank can run them on its own planes
+ * while the halo planes are still arriving over NVLink, then on the halo planes, and finally call pvd_conv_finish for the
+ * x pass, the inverse passes and the density epilogue.  h_act[t] points at plane 0 of volume t (as in pvd_conv_execute).
+ *   dose = gain * conv(sum_t w_t act_t, kernel) / max(rho, rho_min)   (gain = scale * rho_ref; no density: gain = scale)
+ * pvd_conv_execute(...) == pvd_conv_forward_planes(.., gain, 0, n0, ..) followed by pvd_conv_finish(..).  FFT algorithm only;
+ * every input plane must have been forwarded once before pvd_conv_finish. */
+int pvd_conv_forward_planes(pvd_plan* plan, const float* const* h_act, const float* h_weights, int T, float gain,
+                            int plane_lo, int plane_hi, void* stream);
+int pvd_conv_finish(pvd_plan* plan, const float* density, float rho_min, float rho_cut, float* dose, void* stream);
 
 int pvd_plan_destroy(pvd_plan* plan);
 

@@ -21,8 +21,8 @@ MAX_T = 16
 
 # every symbol include/pvdose.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "pvd_version", "pvd_last_error", "pvd_good_fft_size", "pvd_good_fft_size_axis", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
-    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
+    "pvd_version", "pvd_build_id", "pvd_last_error", "pvd_good_fft_size", "pvd_good_fft_size_axis", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
+    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_conv_forward_planes", "pvd_conv_finish", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
     "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
     "pvd_density_scale", "pvd_monoexp_fit", "pvd_ct_prepare", "pvd_roi_minmax", "pvd_dvh_histogram",
     "pvd_stager_create", "pvd_stager_destroy", "pvd_stage_h2d", "pvd_stage_d2h", "pvd_i16_to_f32",
@@ -75,6 +75,7 @@ class PvdLib:
         vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
         d.pvd_version.restype = C.c_int
         d.pvd_last_error.restype = C.c_char_p
+        d.pvd_build_id.restype = C.c_char_p
         d.pvd_good_fft_size.argtypes = [C.c_int]
         d.pvd_good_fft_size_axis.argtypes = [C.c_int, C.c_int]
         d.pvd_plan_create.argtypes = [C.POINTER(vp), ip, ip, C.c_int, C.c_int]
@@ -84,6 +85,8 @@ class PvdLib:
         d.pvd_plan_set_workspace.argtypes = [vp, vp, C.c_size_t, vp]
         d.pvd_plan_set_kernel.argtypes = [vp, vp, vp]
         d.pvd_conv_execute.argtypes = [vp, C.POINTER(vp), fp, C.c_int, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
+        d.pvd_conv_forward_planes.argtypes = [vp, C.POINTER(vp), fp, C.c_int, C.c_float, C.c_int, C.c_int, vp]
+        d.pvd_conv_finish.argtypes = [vp, vp, C.c_float, C.c_float, vp, vp]
         d.pvd_plan_destroy.argtypes = [vp]
         d.pvd_plan_set_profiling.argtypes = [vp, C.c_int]
         d.pvd_plan_get_pass_times.argtypes = [vp, fp, C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.c_int]
@@ -111,6 +114,9 @@ class PvdLib:
 
     def version(self) -> int:
         return self.dll.pvd_version()
+
+    def build_id(self) -> str:
+        return (self.dll.pvd_build_id() or b"").decode()
 
     def good_fft_size(self, n: int, axis: int = 0) -> int:
         return self.dll.pvd_good_fft_size_axis(int(n), int(axis))
@@ -147,6 +153,16 @@ class PvdLib:
         ptrs = (C.c_void_p * T)(*act_ptrs)
         w = (C.c_float * T)(*[float(x) for x in weights]) if weights is not None else None
         self.check(self.dll.pvd_conv_execute(plan, ptrs, w, T, density_ptr, rho_ref, rho_min, rho_cut, scale, dose_ptr, stream))
+
+    def conv_forward_planes(self, plan: int, act_ptrs: Sequence[int], weights: Optional[Sequence[float]], gain: float, lo: int, hi: int,
+                            stream: int = 0):
+        T = len(act_ptrs)
+        ptrs = (C.c_void_p * T)(*act_ptrs)
+        w = (C.c_float * T)(*[float(x) for x in weights]) if weights is not None else None
+        self.check(self.dll.pvd_conv_forward_planes(plan, ptrs, w, T, gain, lo, hi, stream))
+
+    def conv_finish(self, plan: int, density_ptr: Optional[int], rho_min: float, rho_cut: float, dose_ptr: int, stream: int = 0):
+        self.check(self.dll.pvd_conv_finish(plan, density_ptr, rho_min, rho_cut, dose_ptr, stream))
 
     def plan_destroy(self, plan: int):
         self.dll.pvd_plan_destroy(plan)

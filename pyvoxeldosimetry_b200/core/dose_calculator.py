@@ -18,7 +18,6 @@ unless the caller supplies config['registration'] = callable(fixed, moving, spac
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -28,12 +27,40 @@ from .activity_sampler import ActivitySampler
 from .kernel_convolution import KernelConvolutionCalculator, trapezoid_weights
 
 
-@dataclass
 class DoseCalculationResult:
-    absorbed_dose: Optional[np.ndarray]
-    dose_rate_maps: List[np.ndarray]
-    time_points: List[float]
-    metadata: Dict[str, Any]
+    """Same four fields, positional order and repr as the reference's dataclass (core/dose_calculator.py:24-30).
+    `absorbed_dose` may be handed over as a zero-argument callable: it is then evaluated on first access - the
+    single-timepoint physical-decay dose is a full-volume product the caller often never reads (the reference itself
+    returns None there), and a 105 M voxel NumPy multiply would otherwise dominate the call."""
+
+    __slots__ = ("_absorbed", "dose_rate_maps", "time_points", "metadata")
+
+    def __init__(self, absorbed_dose, dose_rate_maps: List[np.ndarray], time_points: List[float], metadata: Dict[str, Any]):
+        self._absorbed = absorbed_dose
+        self.dose_rate_maps = dose_rate_maps
+        self.time_points = time_points
+        self.metadata = metadata
+
+    @property
+    def absorbed_dose(self) -> Optional[np.ndarray]:
+        if callable(self._absorbed):
+            self._absorbed = self._absorbed()
+        return self._absorbed
+
+    @absorbed_dose.setter
+    def absorbed_dose(self, value) -> None:
+        self._absorbed = value
+
+    def __repr__(self) -> str:
+        return (f"DoseCalculationResult(absorbed_dose={self.absorbed_dose!r}, dose_rate_maps={self.dose_rate_maps!r}, "
+                f"time_points={self.time_points!r}, metadata={self.metadata!r})")
+
+    def __eq__(self, other) -> bool:
+        if not isinstance(other, DoseCalculationResult):
+            return NotImplemented
+        return (np.array_equal(self.absorbed_dose, other.absorbed_dose) and len(self.dose_rate_maps) == len(other.dose_rate_maps)
+                and all(np.array_equal(a, b) for a, b in zip(self.dose_rate_maps, other.dose_rate_maps))
+                and list(self.time_points) == list(other.time_points) and self.metadata == other.metadata)
 
 
 class DoseCalculator:
@@ -104,7 +131,7 @@ class DoseCalculator:
                 factor = self.activity_sampler.half_life * f / math.log(2.0)
                 if self.config.get("decay_correct_to_t0") and time_points:
                     factor *= math.exp(math.log(2.0) * float(time_points[0]) / self.activity_sampler.half_life)
-                absorbed = rate * np.float32(factor) if rate.dtype == np.float32 else rate * factor
+                absorbed = (lambda: rate * np.float32(factor)) if rate.dtype == np.float32 else (lambda: rate * factor)
             return DoseCalculationResult(absorbed, [rate], time_points or [], {"mode": "single_timepoint",
                                                                              "time_unit_of_integration": "seconds"})
 

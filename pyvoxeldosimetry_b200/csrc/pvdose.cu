@@ -177,14 +177,7 @@ struct FastRows {
 #define PVD_ROWS_NOPIPE(N, NT, R1, R2, R3) \
     { N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>, nullptr, nullptr, 0 }
 const FastCols kFastCols[] = {
-#ifdef PVD_EXP_Y1632  // experiment build: every 512-point column pass on the two-stage 16*32 register kernel (2 x 256 threads per SM, tile walk)
-    {512, 256,
-     {cols_fast_kernel<512, 256, 16, 32, 1, COL_FWD, 2>, cols_fast_kernel<512, 256, 16, 32, 1, COL_INV, 2>,
-      cols_fast_kernel<512, 256, 16, 32, 1, COL_CONV, 2>, cols_fast_kernel<512, 256, 16, 32, 1, COL_SPEC, 2>},
-     {nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}, {256, 256, 256, 256}},
-#else
     PVD_COLS_CX(512, 512, 1, 8, 8, 8, 256, 2, 16, 32, 1),
-#endif
     PVD_COLS(256, 256, 2, 16, 16, 1),
     PVD_COLS(400, 320, 1, 20, 20, 1),
     PVD_COLS(576, 384, 1, 24, 24, 1),   // 512 + kernel reach ('same' mode of 512-wide volumes)
@@ -192,10 +185,11 @@ const FastCols kFastCols[] = {
     PVD_COLS(288, 288, 2, 16, 18, 1),   // 256 + kernel reach
     PVD_COLS_NOPIPE(1024, 1024, 16, 8, 8),
     // slab decomposition of the 1024 x 1024 x 800 volume ('same' mode): 1024 + reach -> 1152, slabs of
-    // 256 / 128 planes + 50 halo planes -> 320 / 192
+    // 256 / 128 planes + 50 halo planes -> 320 / 180 (192: other kernel sizes)
     PVD_COLS_NOPIPE(1152, 768, 8, 12, 12),
     PVD_COLS(320, 320, 2, 16, 20, 1),
     PVD_COLS(192, 256, 3, 12, 16, 1),
+    PVD_COLS(180, 288, 3, 10, 18, 1),   // 128-plane slab + 50 halo planes = 178 -> 180 (8 ranks; 192 costs 6.7 % more points)
 };
 const FastRows kFastRows[] = {
     PVD_ROWS(400, 320, 2, 20, 20, 1),
@@ -312,7 +306,7 @@ EncodeTiledFn get_encode_tiled() {
 #endif
 
 int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, int T, long long s0, long long s1,
-                    const int ext[3], cudaStream_t stream) {
+                    const int ext[3], cudaStream_t stream, int out_plane0 = 0) {
     RowFwdArgs a;
     memset(&a, 0, sizeof a);
     for (int t = 0; t < T; ++t) {
@@ -325,9 +319,9 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
     a.n0 = ext[0];
     a.n1 = ext[1];
     a.n2 = ext[2];
-    a.out = p->buf();
     a.out_s0 = (long long)p->m[1] * p->Sz;
     a.out_s1 = p->Sz;
+    a.out = p->buf() + (long long)out_plane0 * a.out_s0;
     a.M2 = p->m[2];
     a.Nh = p->Nh;
     a.Llog = p->rowLlog;
@@ -335,6 +329,7 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
     a.st = p->st[2];
     a.dense_in = (s0 == (long long)ext[1] * s1) ? 1 : 0;
     a.dense = (a.dense_in && a.out_s0 == (long long)ext[1] * a.out_s1) ? 1 : 0;
+
     const long long nrows = (long long)ext[0] * ext[1];
     const long long per = 2LL << p->rowLlog;
     const long long nblk = (nrows + per - 1) / per;
@@ -422,12 +417,7 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
     if (p->fastCols[axis]) {
         const FastCols* f = p->fastCols[axis];
         const size_t smem = ((size_t)f->N * 16 + 4 * f->N) * sizeof(float2);
-#ifdef PVD_EXP_Y1632
-        const bool walk = p->fnGrid[axis] > 0 && f->N == 512;
-#else
-        const bool walk = mode == COL_CONV && p->fnGrid[axis] > 0;
-#endif
-        if (walk) {
+        if (mode == COL_CONV && p->fnGrid[axis] > 0) {
             // persistent walk over the tiles with the CTAs that are resident anyway (see cols_fast_kernel); launched
             // normally: as a programmatic dependent this pass measured +70 us per C3 volume
             a.loop_ntz = (p->Nh + 15) / 16;
@@ -615,6 +605,10 @@ int execute_direct(pvd_plan* p, const float* const* h_act, const float* h_weight
 extern "C" {
 
 int pvd_version(void) { return PVD_VERSION; }
+#ifndef PVD_BUILD_ID
+#define PVD_BUILD_ID "unstamped"
+#endif
+const char* pvd_build_id(void) { return PVD_BUILD_ID; }
 const char* pvd_last_error(void) { return g_err.c_str(); }
 int pvd_good_fft_size(int n) { return good_size_axis(n, 0); }
 int pvd_good_fft_size_axis(int n, int axis) { return good_size_axis(n, axis == 2 ? 2 : 0); }
@@ -803,40 +797,86 @@ int pvd_plan_set_kernel(pvd_plan* p, const float* kernel, void* stream_) {
     return PVD_OK;
 }
 
-int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, const float* density,
-                     float rho_ref, float rho_min, float rho_cut, float scale, float* dose, void* stream_) {
-    if (!p || !h_act || !dose) return fail(PVD_ERR_INVALID, "null argument");
+namespace {
+
+// Plane-local forward passes (P1 z R2C + time-weighted sum, P2 y forward) of input planes [lo, hi) into the work buffer.
+// `gain` (scale * rho_ref) rides on the input weights: the convolution is linear, so the last pass's epilogue is just
+// dose = v / max(rho, rho_min) (3 instructions per voxel instead of 6).
+int conv_forward(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, float gain, int lo, int hi,
+                 cudaStream_t stream, bool mark) {
+    const double c = 8.0 * p->Nh;  // bytes of one half-spectrum row
+    float wfold[PVD_MAX_T];
+    const float* act[PVD_MAX_T];
+    const long long plane = (long long)p->n[1] * p->n[2];
+    for (int t = 0; t < T; ++t) {
+        wfold[t] = (h_weights ? h_weights[t] : 1.f) * gain;
+        act[t] = h_act[t] + (long long)lo * plane;
+    }
+    const int ext[3] = {hi - lo, p->n[1], p->n[2]};
+    if (mark) p->mark(stream, "P1 rows_fwd (z R2C + time-weighted sum)", 4.0 * T * ext[0] * p->n[1] * p->n[2] + c * ext[0] * p->n[1]);
+    int rc = launch_rows_fwd(p, act, wfold, T, plane, p->n[2], ext, stream, lo);
+    if (rc) return rc;
+    if (mark) p->mark(stream, "P2 cols y forward", c * ext[0] * ((double)p->n[1] + p->m[1]));
+    return launch_cols(p, 1, COL_FWD, p->buf(), p->buf(), lo, hi - lo, p->n[1], 0, p->m[1], 1.f, stream);
+}
+
+int conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, cudaStream_t stream, bool mark);
+
+int check_execute_state(pvd_plan* p, const float* const* h_act, int T) {
     if (T < 1 || T > PVD_MAX_T) return fail(PVD_ERR_INVALID, "T=%d outside [1,%d]: pre-accumulate with pvd_weighted_sum", T, PVD_MAX_T);
     if (!p->ws) return fail(PVD_ERR_STATE, "workspace not set");
     if (!p->kernel_set) return fail(PVD_ERR_STATE, "dose kernel not set");
     for (int t = 0; t < T; ++t)
         if (!h_act[t]) return fail(PVD_ERR_INVALID, "activity pointer %d is null", t);
+    return PVD_OK;
+}
+
+}  // namespace
+
+int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, const float* density,
+                     float rho_ref, float rho_min, float rho_cut, float scale, float* dose, void* stream_) {
+    if (!p || !h_act || !dose) return fail(PVD_ERR_INVALID, "null argument");
+    if (int rc = check_execute_state(p, h_act, T)) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (p->algo == PVD_ALGO_DIRECT) return execute_direct(p, h_act, h_weights, T, density, rho_ref, rho_min, rho_cut, scale, dose, stream);
-    const double c = 8.0 * p->Nh;  // bytes of one half-spectrum row
-    // The convolution is linear: the output factor scale * rho_ref rides on the input weights the first pass applies
-    // anyway, so the last pass's epilogue is dose = v / max(rho, rho_min) (3 instructions per voxel instead of 6).
-    float wfold[PVD_MAX_T];
-    const float out_factor = scale * (density ? rho_ref : 1.f);
-    for (int t = 0; t < T; ++t) wfold[t] = (h_weights ? h_weights[t] : 1.f) * out_factor;
-    h_weights = wfold;
-    scale = 1.f;
-    rho_ref = 1.f;
     p->npass = 0;
-    p->mark(stream, "P1 rows_fwd (z R2C + time-weighted sum)", 4.0 * T * p->n[0] * p->n[1] * p->n[2] + c * p->n[0] * p->n[1]);
-    int rc = launch_rows_fwd(p, h_act, h_weights, T, (long long)p->n[1] * p->n[2], p->n[2], p->n, stream);
-    if (rc) return rc;
-    p->mark(stream, "P2 cols y forward", c * p->n[0] * ((double)p->n[1] + p->m[1]));
-    rc = launch_cols(p, 1, COL_FWD, p->buf(), p->buf(), 0, p->n[0], p->n[1], 0, p->m[1], 1.f, stream);
-    if (rc) return rc;
-    p->mark(stream, "P3 cols x forward*spectrum*inverse", c * p->m[1] * ((double)p->n[0] + p->m[0] + p->on[0]));
+    if (int rc = conv_forward(p, h_act, h_weights, T, scale * (density ? rho_ref : 1.f), 0, p->n[0], stream, true)) return rc;
+    return conv_finish(p, density, rho_min, rho_cut, dose, stream, true);
+}
+
+int pvd_conv_forward_planes(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, float gain, int plane_lo,
+                            int plane_hi, void* stream_) {
+    if (!p || !h_act) return fail(PVD_ERR_INVALID, "null argument");
+    if (int rc = check_execute_state(p, h_act, T)) return rc;
+    if (p->algo != PVD_ALGO_FFT) return fail(PVD_ERR_UNSUPPORTED, "the split form exists for the FFT algorithm only");
+    if (plane_lo < 0 || plane_hi > p->n[0] || plane_lo > plane_hi)
+        return fail(PVD_ERR_INVALID, "plane range [%d, %d) outside [0, %d)", plane_lo, plane_hi, p->n[0]);
+    if (plane_lo == plane_hi) return PVD_OK;
+    return conv_forward(p, h_act, h_weights, T, gain, plane_lo, plane_hi, (cudaStream_t)stream_, false);
+}
+
+int pvd_conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, void* stream_) {
+    if (!p || !dose) return fail(PVD_ERR_INVALID, "null argument");
+    if (!p->ws) return fail(PVD_ERR_STATE, "workspace not set");
+    if (!p->kernel_set) return fail(PVD_ERR_STATE, "dose kernel not set");
+    if (p->algo != PVD_ALGO_FFT) return fail(PVD_ERR_UNSUPPORTED, "the split form exists for the FFT algorithm only");
+    return conv_finish(p, density, rho_min, rho_cut, dose, (cudaStream_t)stream_, false);
+}
+
+namespace {
+
+int conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, cudaStream_t stream, bool mark) {
+    const double c = 8.0 * p->Nh;
+    const float rho_ref = 1.f, scale = 1.f;  // folded into the input weights by conv_forward
+    int rc;
+    if (mark) p->mark(stream, "P3 cols x forward*spectrum*inverse", c * p->m[1] * ((double)p->n[0] + p->m[0] + p->on[0]));
     rc = launch_cols(p, 0, COL_CONV, p->buf(), p->buf(), 0, p->m[1], p->n[0], p->olo[0], p->on[0], 1.f, stream);
     if (rc) return rc;
-    p->mark(stream, "P4 cols y inverse", c * p->on[0] * ((double)p->m[1] + p->on[1]));
+    if (mark) p->mark(stream, "P4 cols y inverse", c * p->on[0] * ((double)p->m[1] + p->on[1]));
     rc = launch_cols(p, 1, COL_INV, p->buf(), p->buf(), p->olo[0], p->on[0], p->m[1], p->olo[1], p->on[1], 1.f, stream);
     if (rc) return rc;
-    p->mark(stream, "P5 rows_inv (z C2R + density + crop)",
-            c * p->on[0] * p->on[1] + (density ? 8.0 : 4.0) * p->on[0] * p->on[1] * p->on[2]);
+    if (mark) p->mark(stream, "P5 rows_inv (z C2R + density + crop)",
+                      c * p->on[0] * p->on[1] + (density ? 8.0 : 4.0) * p->on[0] * p->on[1] * p->on[2]);
     RowInvArgs a;
     memset(&a, 0, sizeof a);
     a.in = p->buf();
@@ -868,6 +908,7 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
                   ? 1
                   : 0;
     a.plain_den = (density && rho_cut <= 0.f) ? 1 : 0;  // scale * rho_ref == 1 by the folding above
+
     a.vec4 = (p->on[2] % 4 == 0 && a.out_s0 % 4 == 0 && a.out_s1 % 4 == 0 && ((uintptr_t)dose & 15) == 0 &&
               (!density || (((uintptr_t)density & 15) == 0 && a.den_s0 % 4 == 0 && a.den_s1 % 4 == 0)))
                  ? 1
@@ -917,7 +958,7 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
 #endif
         PVD_LAUNCH_PDL(p->pdl, f->invPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
         PVD_CUDA_CHECK("rows_inv_pipe_kernel");
-        p->mark_end(stream);
+        if (mark) p->mark_end(stream);
         return PVD_OK;
     }
     if (p->fastRows) {
@@ -925,14 +966,16 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
         const size_t smem = ((size_t)f->N * 17 + 4 * f->N) * sizeof(float2);
         PVD_LAUNCH(f->inv, dim3((unsigned)((nrows + 31) / 32)), dim3(f->NT), smem, stream, a);
         PVD_CUDA_CHECK("rows_inv_fast_kernel");
-        p->mark_end(stream);
+        if (mark) p->mark_end(stream);
         return PVD_OK;
     }
     PVD_LAUNCH(rows_inv_kernel, dim3((unsigned)((nrows + per - 1) / per)), dim3(PVD_BLOCK), p->rowSmem, stream, a);
     PVD_CUDA_CHECK("rows_inv_kernel");
-    p->mark_end(stream);
+    if (mark) p->mark_end(stream);
     return PVD_OK;
 }
+
+}  // namespace
 
 int pvd_plan_set_profiling(pvd_plan* p, int enable) {
     if (!p) return fail(PVD_ERR_INVALID, "null argument");

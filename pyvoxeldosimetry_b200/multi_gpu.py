@@ -1,13 +1,17 @@
 """Multi-GPU partitioning of the dose path (one process per GPU, torch.distributed / NCCL over NVLink).
 
-Two ways the path shards:
+Two ways the path shards (the reference itself is single-process, core/kernel_convolution.py:48-76):
   1. independent patient volumes / timepoint sets -> `shard_range`: no data-path collective at all;
-  2. one very large volume -> contiguous slabs along axis 0 (the slowest memory axis of the C-order
-     arr[x, y, z] layout) with a kernel-radius halo exchanged between neighbouring ranks
-     (`exchange_halos`: batched isend/irecv = ncclSend/ncclRecv pairs in one group), then an ordinary
-     local convolution on slab+halo that keeps only its interior planes (overlap-save).  No distributed
-     FFT / all-to-all is ever needed.
-Only index logic and point-to-point exchange live here; the arithmetic is ConvPlan (CUDA).
+  2. one very large volume -> contiguous slabs along axis 0 (the slowest memory axis of the C-order arr[x, y, z] layout)
+     with a kernel-radius halo exchanged between neighbouring ranks, then an ordinary local convolution on slab+halo
+     that keeps only its interior planes (overlap-save).  No distributed FFT / all-to-all is ever needed.
+
+`halo_plan` is the pure index logic (who sends which planes to whom, where they land); `SlabConvolver` owns ONE
+preallocated slab-plus-halo buffer per rank, receives straight into views of it and sends straight from views of it
+(plane ranges are contiguous memory: no staging copies, no per-call allocation), issues the exchange on a side stream
+and runs the plane-local forward passes of its own planes (pvd_conv_forward_planes) while the halo planes are in
+flight; the halo planes get the same passes on arrival, then pvd_conv_finish runs the x pass and the inverse passes.
+Only index logic and point-to-point exchange live here; the arithmetic is libpvdose (CUDA).
 """
 from __future__ import annotations
 
@@ -90,77 +94,100 @@ def _segments(need_lo: int, need_hi: int, n0: int, wrap: bool) -> List[Tuple[int
     return out
 
 
-def exchange_halos(local: torch.Tensor, shape0: int, boundary: str, kshape0: int, group=None) -> torch.Tensor:
-    """local: this rank's own planes [B, n1, n2] (global planes [lo, hi)).  Returns the slab-plus-halo
-    tensor the local plan consumes.  Point-to-point only: every needed plane range is intersected with
-    every peer's owned range, so halos wider than a neighbour's slab are handled too."""
-    import torch.distributed as dist
+def _needs(bounds, r: int, shape0: int, boundary: str, kshape0: int) -> Tuple[int, int]:
+    lo, hi = bounds[r]
+    if boundary == "reference":
+        return lo - (min(kshape0, shape0) - 1), hi
+    c0 = kshape0 // 2
+    return lo - (kshape0 - 1 - c0), hi + c0
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+
+def halo_plan(shape0: int, world: int, boundary: str, kshape0: int) -> List[Dict]:
+    """Exchange schedule of every rank (pure index logic).  Entry r:
+         own    (lo, hi)        global planes rank r owns
+         need   (nlo, nhi)      global plane range of its slab-plus-halo buffer (wraps / sticks out of [0, n0))
+         own_off                offset of its own planes inside that buffer
+         recvs  [(peer, dst_off, count)]            planes arriving from `peer` land at buffer planes [dst_off, dst_off+count)
+         sends  [(peer, src_off, count)]            buffer planes [src_off, ...) (inside the own range) go to `peer`
+         copies [(src_off, dst_off, count)]         planes of its own slab it needs again elsewhere (circular wrap onto itself)
+       Every needed range is intersected with every rank's owned range, so halos wider than a neighbour's slab work too.
+       recvs of rank r from peer p and sends of p to r list the same pieces in the same order (NCCL matches them in order)."""
+    if boundary not in ("reference", "same"):
+        raise ValueError(f"unknown boundary mode {boundary!r}")
     bounds = slab_bounds(shape0, world)
     wrap = boundary == "reference"
-
-    def needs(r):
+    plans = []
+    for r in range(world):
         lo, hi = bounds[r]
-        if wrap:
-            h = min(kshape0, shape0) - 1
-            return lo - h, hi
-        c0 = kshape0 // 2
-        return lo - (kshape0 - 1 - c0), hi + c0
+        nlo, nhi = _needs(bounds, r, shape0, boundary, kshape0)
+        plans.append(dict(own=(lo, hi), need=(nlo, nhi), own_off=lo - nlo, recvs=[], sends=[], copies=[]))
+    for r in range(world):
+        nlo, nhi = plans[r]["need"]
+        lo, hi = bounds[r]
+        for dst_off, glo, ghi in _segments(nlo, nhi, shape0, wrap):
+            for peer, (plo, phi) in enumerate(bounds):
+                a, b = max(glo, plo), min(ghi, phi)
+                if a >= b:
+                    continue
+                d0 = dst_off + (a - glo)
+                if peer == r:
+                    src = plans[r]["own_off"] + (a - lo)
+                    if src != d0:  # the own planes themselves sit at own_off already
+                        plans[r]["copies"].append((src, d0, b - a))
+                else:
+                    plans[r]["recvs"].append((peer, d0, b - a))
+                    plans[peer]["sends"].append((r, plans[peer]["own_off"] + (a - plo), b - a))
+    return plans
 
-    my_lo, my_hi = bounds[rank]
-    nlo, nhi = needs(rank)
+
+def exchange_halos(local: torch.Tensor, shape0: int, boundary: str, kshape0: int, group=None) -> torch.Tensor:
+    """local: this rank's own planes [B, n1, n2] (global planes [lo, hi)).  Returns a NEW slab-plus-halo tensor (the
+    allocation-free form is SlabConvolver).  Point-to-point only."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    plan = halo_plan(shape0, world, boundary, kshape0)[rank]
+    nlo, nhi = plan["need"]
     out = torch.zeros((nhi - nlo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    ops, recvs = [], []
-    # receives: pieces of my needed range owned by peers (or myself)
-    for dst_off, glo, ghi in _segments(nlo, nhi, shape0, wrap):
-        for peer, (plo, phi) in enumerate(bounds):
-            a, b = max(glo, plo), min(ghi, phi)
-            if a >= b:
-                continue
-            d0 = dst_off + (a - glo)
-            if peer == rank:
-                out[d0 : d0 + (b - a)].copy_(local[a - my_lo : b - my_lo])
-            else:
-                buf = torch.empty((b - a,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-                recvs.append((buf, d0))
-                ops.append(dist.P2POp(dist.irecv, buf, peer, group))
-    # sends: pieces of every peer's needed range that I own
-    keep = []
-    for peer in range(world):
-        if peer == rank:
-            continue
-        plo_n, phi_n = needs(peer)
-        for _, glo, ghi in _segments(plo_n, phi_n, shape0, wrap):
-            a, b = max(glo, my_lo), min(ghi, my_hi)
-            if a >= b:
-                continue
-            piece = local[a - my_lo : b - my_lo].contiguous()
-            keep.append(piece)
-            ops.append(dist.P2POp(dist.isend, piece, peer, group))
-    if ops:
-        # order recvs/sends deterministically per pair: batch_isend_irecv groups them (ncclGroupStart/End)
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    for buf, d0 in recvs:
-        out[d0 : d0 + buf.shape[0]].copy_(buf)
+    off = plan["own_off"]
+    out[off : off + local.shape[0]].copy_(local)
+    for req in _post_exchange(out, plan, group):
+        req.wait()
+    for src, dst, cnt in plan["copies"]:
+        out[dst : dst + cnt].copy_(out[src : src + cnt])
     return out
+
+
+def _post_exchange(buf: torch.Tensor, plan: Dict, group=None) -> list:
+    """Post every receive (into views of `buf`) and send (from views of `buf`) of `plan` as ONE batch
+    (= ncclGroupStart/End around ncclSend/ncclRecv).  Returns the request handles."""
+    import torch.distributed as dist
+
+    ops = [dist.P2POp(dist.irecv, buf[d0 : d0 + cnt], peer, group) for peer, d0, cnt in plan["recvs"]]
+    ops += [dist.P2POp(dist.isend, buf[s0 : s0 + cnt], peer, group) for peer, s0, cnt in plan["sends"]]
+    return dist.batch_isend_irecv(ops) if ops else []
 
 
 class SlabConvolver:
     """Rank-local half of a slab-decomposed convolution (CUDA).  Usage on every rank:
         sc = SlabConvolver(global_shape, kernel, boundary)          # after init_process_group('nccl')
-        dose_slab = sc(local_activity_slab, density_slab=None)      # global planes [sc.lo, sc.hi)
-    """
+        sc.interior.copy_(my_planes)   # or hand `local=` to the call; sc.interior is a view of the slab+halo buffer
+        dose_slab = sc(density_slab=rho_slab)                       # global planes [sc.lo, sc.hi)
+    `rank=` / `world=` given explicitly build the geometry without a process group (single-GPU emulation of every
+    rank in turn: tests, 1-GPU runs); halos are then filled with `fill_from_global`."""
 
-    def __init__(self, shape: Sequence[int], kernel, boundary: str = "same", group=None, device=None):
-        import torch.distributed as dist
-
+    def __init__(self, shape: Sequence[int], kernel, boundary: str = "same", group=None, device=None,
+                 rank: Optional[int] = None, world: Optional[int] = None):
         from .engine import ConvPlan, require_cuda, to_device_f32
 
         self.group = group
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.distributed = rank is None
+        if self.distributed:
+            import torch.distributed as dist
+
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:
+            self.world, self.rank = int(world), int(rank)
         self.shape = tuple(int(s) for s in shape)
         self.boundary = boundary
         self.device = require_cuda(device)
@@ -168,13 +195,73 @@ class SlabConvolver:
         self.kshape = tuple(kdev.shape)
         self.geom = slab_geometry(self.shape, self.kshape, boundary, self.world, self.rank)
         self.lo, self.hi = self.geom["lo"], self.geom["hi"]
+        self.hplan = halo_plan(self.shape[0], self.world, boundary, self.kshape[0])[self.rank]
         kc = self.geom["kcrop"]
         kdev = kdev[: kc[0], : kc[1], : kc[2]].contiguous()
         self.plan = ConvPlan(self.geom["n"], kc, boundary, self.device, ex=self.geom["ex"])
         self.plan.set_kernel(kdev)
+        # ONE slab-plus-halo buffer for the life of the object; halo planes outside the volume ('same' mode at the ends)
+        # are zero once and never written again
+        self.padded = torch.zeros(self.geom["n"], dtype=torch.float32, device=self.device)
+        off, B = self.hplan["own_off"], self.hi - self.lo
+        self.interior = self.padded[off : off + B]
+        self.out = torch.empty(self.plan.out_shape, dtype=torch.float32, device=self.device)
+        self.comm_stream = torch.cuda.Stream(self.device)
+        self.exchange_ms_events = None
 
-    def __call__(self, local: torch.Tensor, density_slab: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
-        if tuple(local.shape) != (self.hi - self.lo,) + self.shape[1:]:
-            raise ValueError("local slab has the wrong shape")
-        padded = exchange_halos(local, self.shape[0], self.boundary, self.kshape[0], self.group)
-        return self.plan.execute([padded], None, density_slab, **kw)
+    # -------------------------------------------------------------- emulation helper (no process group)
+    def fill_from_global(self, volume: torch.Tensor) -> None:
+        """Fill the whole slab-plus-halo buffer from a global device volume (what the exchange delivers)."""
+        nlo, nhi = self.hplan["need"]
+        n0 = self.shape[0]
+        for dst_off, glo, ghi in _segments(nlo, nhi, n0, self.boundary == "reference"):
+            self.padded[dst_off : dst_off + (ghi - glo)].copy_(volume[glo:ghi])
+
+    # -------------------------------------------------------------- one convolution
+    def __call__(self, local: Optional[torch.Tensor] = None, density_slab: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None, exchange: bool = True, overlap: bool = True, rho_ref: float = 1.0,
+                 rho_min: float = 0.1, rho_cut: float = 0.0, scale: float = 1.0) -> torch.Tensor:
+        B = self.hi - self.lo
+        if local is not None:
+            if tuple(local.shape) != (B,) + self.shape[1:]:
+                raise ValueError("local slab has the wrong shape")
+            if local.data_ptr() != self.interior.data_ptr():
+                self.interior.copy_(local)
+        if density_slab is not None and tuple(density_slab.shape) != self.plan.out_shape:
+            raise ValueError("density slab has the wrong shape")
+        out = self.out if out is None else out
+        lib, h = self.plan.lib, self.plan.handle
+        main = torch.cuda.current_stream(self.device)
+        off, L = self.hplan["own_off"], self.geom["n"][0]
+        gain = float(scale) * (float(rho_ref) if density_slab is not None else 1.0)
+        ptr = [self.padded.data_ptr()]
+        with torch.cuda.device(self.device):
+            reqs = []
+            if exchange and self.distributed and (self.hplan["recvs"] or self.hplan["sends"]):
+                # the exchange runs on its own stream: it needs the interior planes (sends) but nothing else
+                self.comm_stream.wait_stream(main)
+                with torch.cuda.stream(self.comm_stream):
+                    reqs = _post_exchange(self.padded, self.hplan, self.group)
+                if not overlap:
+                    for r in reqs:
+                        r.wait()
+                    reqs = []
+            if exchange:
+                for src, dst, cnt in self.hplan["copies"]:
+                    self.padded[dst : dst + cnt].copy_(self.padded[src : src + cnt])
+            if reqs:
+                # own planes first, while the halo planes are in flight ...
+                lib.conv_forward_planes(h, ptr, None, gain, off, off + B, main.cuda_stream)
+                for r in reqs:
+                    r.wait()  # stream-level: `main` waits for the NCCL work, the host does not
+                # ... then the halo planes below and above
+                lib.conv_forward_planes(h, ptr, None, gain, 0, off, main.cuda_stream)
+                lib.conv_forward_planes(h, ptr, None, gain, off + B, L, main.cuda_stream)
+            else:
+                lib.conv_forward_planes(h, ptr, None, gain, 0, L, main.cuda_stream)
+            lib.conv_finish(h, None if density_slab is None else density_slab.data_ptr(), float(rho_min), float(rho_cut),
+                            out.data_ptr(), main.cuda_stream)
+        return out
+
+    def check_device_errors(self) -> None:
+        self.plan.check_device_errors()

@@ -74,3 +74,51 @@ def test_slab_halo_exchange_gloo(world, boundary, shape, kshape):
     ref = orc.conv_reference(a, k) if boundary == "reference" else orc.conv_same(a, k)
     assert orc.rel_err_of_peak(full, ref) <= 1e-4
     assert owned == list(range(7))
+
+
+@pytest.mark.parametrize("boundary", ["reference", "same"])
+@pytest.mark.parametrize("n0,world,k0", [(12, 2, 5), (9, 3, 7), (7, 3, 6), (64, 8, 51), (16, 1, 5), (10, 4, 64), (1024, 8, 51)])
+def test_halo_plan_delivers_every_needed_plane_exactly_once(boundary, n0, world, k0):
+    """Pure index logic: executing every rank's schedule on host arrays must reproduce the wrapped / zero-padded plane
+    range each rank's local plan expects, with matching send / receive lists per pair."""
+    from pyvoxeldosimetry_b200.multi_gpu import halo_plan, slab_bounds
+
+    if n0 < world:
+        pytest.skip("more ranks than planes")
+    plans = halo_plan(n0, world, boundary, k0)
+    bounds = slab_bounds(n0, world)
+    vol = np.arange(1, n0 + 1, dtype=np.float64)  # plane id + 1 (0 = zero padding)
+    bufs = []
+    for r, p in enumerate(plans):
+        nlo, nhi = p["need"]
+        b = np.zeros(nhi - nlo)
+        lo, hi = bounds[r]
+        assert p["own"] == (lo, hi) and p["own_off"] == lo - nlo
+        b[p["own_off"] : p["own_off"] + hi - lo] = vol[lo:hi]
+        bufs.append(b)
+    seen = [np.zeros(len(b), dtype=int) for b in bufs]
+    for r, p in enumerate(plans):
+        seen[r][p["own_off"] : p["own_off"] + bounds[r][1] - bounds[r][0]] += 1
+        # pairwise matching: the k-th receive of r from peer is the k-th send of peer to r
+        for peer in range(world):
+            rec = [(d, c) for (q, d, c) in p["recvs"] if q == peer]
+            snd = [(s, c) for (q, s, c) in plans[peer]["sends"] if q == r]
+            assert [c for _, c in rec] == [c for _, c in snd]
+            for (d, c), (s, _) in zip(rec, snd):
+                po = plans[peer]["own_off"]
+                assert po <= s and s + c <= po + bounds[peer][1] - bounds[peer][0]  # sends come from the peer's own planes
+                bufs[r][d : d + c] = bufs[peer][s : s + c]
+                seen[r][d : d + c] += 1
+        for s, d, c in p["copies"]:
+            bufs[r][d : d + c] = bufs[r][s : s + c]
+            seen[r][d : d + c] += 1
+    for r, p in enumerate(plans):
+        nlo, nhi = p["need"]
+        g = np.arange(nlo, nhi)
+        if boundary == "reference":
+            want = vol[np.mod(g, n0)]
+            assert (seen[r] == 1).all()
+        else:
+            want = np.where((g >= 0) & (g < n0), vol[np.clip(g, 0, n0 - 1)], 0.0)
+            assert (seen[r][(g >= 0) & (g < n0)] == 1).all() and (seen[r][(g < 0) | (g >= n0)] == 0).all()
+        assert np.array_equal(bufs[r], want)

@@ -190,6 +190,8 @@ FAST_CASES = [
     ((1152, 2, 4), (5, 1, 2), 0, 1, True),     # slab-decomposition sizes: x <1152> 8*12*12 (one tile per CTA)
     ((2, 320, 6), (1, 7, 2), 0, 1, False),     # y <320> 16*20
     ((192, 3, 4), (9, 2, 1), 0, 2, True),      # x <192> 12*16 (guarded second stage)
+    ((180, 3, 4), (9, 2, 1), 0, 1, True),      # x <180> 10*18: the 8-rank slab of the 1024-plane volume (128 + 50 halo planes)
+    ((2, 180, 6), (1, 7, 2), 0, 1, False),     # y <180>, persistent pipelined form
     ((3, 5, 800), (2, 2, 9), 0, 1, True),      # rows <800> 8*10*10, pipelined, one CTA per SM
     ((2, 6, 840), (1, 3, 25), 1, 1, True),     # rows <864> 8*9*12: same mode 840 -> 864, no staging pipeline
 ]

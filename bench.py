@@ -143,28 +143,40 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def bind_to_gpu_numa(local: int) -> str:
+def bind_to_gpu_numa(local: int, nlocal: int = 1) -> str:
     """One rank per GPU: run this rank's host threads (and so its pinned staging buffers, first touch) on the CPUs
     of the GPU's own NUMA node, so that host<->device copies of different ranks do not share one socket's memory
-    controllers / inter-socket link.  Best effort; returns a note for stderr."""
+    controllers / inter-socket link.  Ranks whose GPUs hang off the same node split that node's CPUs between them, so
+    that the staging threads of the end-to-end leg (8 per rank at most) do not oversubscribe the cores.  Best effort;
+    returns a note for stderr."""
     try:
         import torch
 
-        p = torch.cuda.get_device_properties(local)
-        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
-            spec = f.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            if "-" in part:
-                a, b = part.split("-")
-                cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
+        def cpulist(idx):
+            p = torch.cuda.get_device_properties(idx)
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+                spec = f.read().strip()
+            cpus = set()
+            for part in spec.split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+            return bdf, spec, cpus
+
+        bdf, spec, cpus = cpulist(local)
         cpus &= os.sched_getaffinity(0)
         if cpus:
-            os.sched_setaffinity(0, cpus)
-            return f"rank on GPU {local} ({bdf}) bound to {len(cpus)} local CPUs ({spec})"
+            sharers = [r for r in range(nlocal) if cpulist(r)[2] & cpus] if nlocal > 1 else [local]
+            mine = sorted(cpus)
+            if len(sharers) > 1 and len(mine) >= 2 * len(sharers):
+                k = sharers.index(local)
+                per = len(mine) // len(sharers)
+                mine = mine[k * per : (k + 1) * per]
+            os.sched_setaffinity(0, set(mine))
+            return f"rank on GPU {local} ({bdf}) bound to {len(mine)} of the {len(cpus)} local CPUs ({spec}; {len(sharers)} rank(s) share the node)"
         return f"GPU {local} ({bdf}): no usable local CPUs in {spec!r}"
     except Exception as e:  # sysfs layout / permissions differ: keep the default affinity
         return f"NUMA binding skipped: {e}"
@@ -178,38 +190,6 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_time(wl, budget_s: float, acts, rho, kernel64):
-    """Literal reference operator (oracle.conv_reference == core/kernel_convolution.py:71-74, float64,
-    single-threaded np.fft) on a bounded sub-volume of the workload.  Returns (voxels/s, sample text, seconds)."""
-    from oracle import dose_oracle as orc
-
-    full = wl["shape"]
-    cands = [full]
-    s = list(full)
-    for ax in (2, 1, 0, 2, 1, 0):
-        s = list(s)
-        s[ax] = max(8, s[ax] // 2)
-        cands.append(tuple(s))
-    # calibrate on the smallest candidate
-    small = cands[-1]
-    a = acts[0][: small[0], : small[1], : small[2]].astype(np.float64)
-    t0 = time.perf_counter()
-    orc.conv_reference(a, kernel64)
-    rate = a.size / (time.perf_counter() - t0)  # voxels/s, optimistic for the bigger ones
-    pick = small
-    for c in cands:
-        if np.prod(c) / rate * 1.6 <= budget_s:
-            pick = c
-            break
-    subs = [np.ascontiguousarray(m[: pick[0], : pick[1], : pick[2]]).astype(np.float64) for m in acts]
-    t0 = time.perf_counter()
-    d = reference_step(subs, kernel64, None if rho is None else rho[: pick[0], : pick[1], : pick[2]])
-    dt = time.perf_counter() - t0
-    what = "literal np.fft.ifftn(fftn(a)*fftn(k,a.shape)).real float64" if len(acts) == 1 else \
-        f"literal calculate_absorbed_dose loop: {len(acts)} np.fft convolutions + trapezoid (core/kernel_convolution.py:94-106)"
-    return subs[0].size / dt, f"{what} on a {pick[0]}x{pick[1]}x{pick[2]} sub-volume", dt
-
-
 def cpu_threaded_time(wl, acts, rho, kernel64, pick):
     """the same mathematics with every host thread - scipy.fft real transforms,
     workers = all cores (oracle.conv_reference_fast) - on the same sub-volume as the literal run.  Best of 2.
@@ -341,6 +321,257 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------
+def link_peak(world: int):
+    """Bare pinned cudaMemcpyAsync ceiling of the box measured by scripts/link_peak.py (profiles/r02_link_peak_<N>gpu.json):
+    per-rank H2D / D2H GB/s when all `world` ranks copy at once.  None when no file exists for this N."""
+    p = os.path.join(REPO, "profiles", f"r02_link_peak_{world}gpu.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"h2d_gbs_per_rank": d["h2d_GBs_aggregate"] / world, "d2h_gbs_per_rank": d["d2h_GBs_aggregate"] / world,
+            "concurrent_gbs_per_rank_each_way": d["h2d_d2h_concurrent_GBs_aggregate_each_way"] / world, "source": os.path.basename(p)}
+
+
+def measure_e2e(wl, args, calc, plan, acts_h, rho_h, dev, dist, world, barrier):
+    """The same metric end to end: HOST buffers in, HOST dose map out, every copy inside the timed region.
+    Headline = the reference's own calling convention: DoseCalculator.calculate_dose with pageable
+    NumPy arrays, one blocking call per volume, the result a fresh ndarray.  The other variants (16-bit inputs as
+    scanners store them, pinned buffers, the pipelined batch call) are reported beside it in variants_ms."""
+    import torch
+
+    from pyvoxeldosimetry_b200 import DoseCalculator
+
+    vox = (float(wl["voxel"]),) * 3
+    shape = wl["shape"]
+    nvox = int(np.prod(shape))
+    reps = max(3, min(args.steps, 8))
+    front = DoseCalculator(wl["nuclide"], "kernel", {"kernel_grid": wl["kgrid"], "boundary": args.boundary, "device": str(dev),
+                                                      "kernel_resolution": wl["voxel"], "tissue_name": "water"})
+    a32 = acts_h[0]
+    variants, bytes_of = {}, {}
+
+    def timed(name, fn, h2d, d2h, n_per_call=1):
+        fn()
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / (reps * n_per_call)
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        variants[name] = float(t.item()) * 1e3
+        bytes_of[name] = (int(h2d), int(d2h))
+        return r
+
+    if wl["T"] == 1:
+        den = {"tissue_densities": rho_h} if rho_h is not None else {}
+        nden = nvox * 4 if rho_h is not None else 0
+        head = "front_door_f32_ndarray" + ("_density_f32_ndarray" if rho_h is not None else "")
+        res = timed(head, lambda: front.calculate_dose(activity_maps=[a32], time_points=[2.0], voxel_size=vox, **den).dose_rate_maps[0],
+                    nvox * 4 + nden, nvox * 4)
+        assert isinstance(res, np.ndarray) and res.shape == tuple(shape)
+        a64 = a32.astype(np.float64)
+        timed("front_door_f64_ndarray" + ("_density_f32_ndarray" if rho_h is not None else ""),
+              lambda: front.calculate_dose(activity_maps=[a64], time_points=[2.0], voxel_size=vox, **den).dose_rate_maps[0], nvox * 4 + nden, nvox * 4)
+        del a64
+        if rho_h is not None:
+            timed("front_door_f32_ndarray_no_density", lambda: front.calculate_dose(activity_maps=[a32], time_points=[2.0], voxel_size=vox).dose_rate_maps[0],
+                  nvox * 4, nvox * 4)
+            # the CT as scanners store it: int16 Hounsfield units (2 bytes per voxel over the link), density derived on the device
+            # (HU -1000 / -700 / 32 / 350 <-> 0.00129 / 0.26 / 1.04 / 1.42 g/cm3 through tissue.HU_KNOTS)
+            hu_h = np.full(shape, -1000, dtype=np.int16)
+            hu_h[rho_h > 0.2] = -700
+            hu_h[rho_h > 1.0] = 32
+            hu_h[rho_h > 1.4] = 350
+            kc = front.calculator
+            timed("calculator_f32_ndarray_ct_i16_ndarray", lambda: kc.calculate_dose_rate(a32, vox, ct_hu=hu_h), nvox * 6, nvox * 4)
+            # PET as DICOM stores it: 16-bit values + rescale slope (io/dicom.py:27-47)
+            slope = float(a32.max()) / 32000.0
+            st16 = np.clip(np.rint(a32 / slope), 0, 32767).astype(np.int16)
+            timed("calculator_i16_ndarray_rescale_ct_i16_ndarray", lambda: kc.calculate_dose_rate(st16, vox, ct_hu=hu_h, rescale=(slope, 0.0)), nvox * 4, nvox * 4)
+            # pinned buffers + the pipelined batch call (H2D of volume i+1, convolution of i, D2H of i-1 overlap)
+            nb = 8
+            pin = lambda x: torch.from_numpy(x).pin_memory()
+            p_a, p_rho, p_hu, p_st = pin(a32), pin(rho_h), pin(hu_h), pin(st16)
+            outs = [torch.empty(tuple(shape), dtype=torch.float32).pin_memory() for _ in range(2)]
+            bo = [outs[i & 1] for i in range(nb)]
+            timed("batch_pinned_f32_density_f32", lambda: kc.calculate_dose_rate_batch([p_a] * nb, vox, [p_rho] * nb, bo), nvox * 8, nvox * 4, nb)
+            timed("batch_pinned_f32_ct_i16", lambda: kc.calculate_dose_rate_batch([p_a] * nb, vox, None, bo, ct_hu=[p_hu] * nb), nvox * 6, nvox * 4, nb)
+            timed("batch_pinned_i16_rescale_ct_i16", lambda: kc.calculate_dose_rate_batch([p_st] * nb, vox, None, bo, ct_hu=[p_hu] * nb, rescale=(slope, 0.0)),
+                  nvox * 4, nvox * 4, nb)
+            del p_a, p_rho, p_hu, p_st, outs, bo
+        api = ("DoseCalculator.calculate_dose(activity_maps=[float32 ndarray], time_points=[t], voxel_size, tissue_densities=float32 ndarray)"
+               ".dose_rate_maps[0] -> ndarray; pageable NumPy arrays, one blocking call per volume")
+    else:
+        kc = front.calculator
+        times = [4.0, 24.0, 96.0, 168.0][: wl["T"]]
+        head = f"calculator_absorbed_dose_{wl['T']}x_f32_ndarray"
+        timed(head, lambda: kc.calculate_absorbed_dose(acts_h, times, vox), nvox * 4 * wl["T"], nvox * 4)
+        api = "KernelConvolutionCalculator.calculate_absorbed_dose(list of float32 ndarrays, time_points, voxel_size) -> ndarray"
+    ms = variants[head]
+    h2d, d2h = bytes_of[head]
+    lp = link_peak(world)
+    out = {"value": world / (ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms, "api": api,
+           "headline_variant": head, "variants_ms": {k: round(v, 3) for k, v in variants.items()},
+           "variants_bytes": {k: {"h2d": b[0], "d2h": b[1]} for k, b in bytes_of.items()}}
+    if lp:
+        # a blocking call cannot overlap its own upload and download: ideal = H2D bytes / H2D peak + D2H bytes / D2H peak
+        ideal = (h2d / lp["h2d_gbs_per_rank"] + d2h / lp["d2h_gbs_per_rank"]) / 1e6
+        out["link"] = dict(lp, ideal_ms_serial=round(ideal, 3), link_frac=round(ideal / ms, 3))
+        best_b = min((k for k in variants if k.startswith("batch_")), key=lambda k: variants[k], default=None)
+        if best_b:
+            bh, bd = bytes_of[best_b]
+            idealb = max(bh, bd) / lp["concurrent_gbs_per_rank_each_way"] / 1e6  # pipelined: both directions at once
+            out["link"]["best_pipelined_variant"] = {"name": best_b, "ms": round(variants[best_b], 3), "ideal_ms": round(idealb, 3),
+                                                     "link_frac": round(idealb / variants[best_b], 3)}
+    front.calculator._plans.clear()
+    return out
+
+
+def time_steps(step, steps, warmup, dev, dist):
+    """CUDA-event time of `steps` calls after `warmup`, barrier + synchronize on both sides, max over ranks (ms per step)."""
+    import torch
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_c4(args, dev, dist, rank, world, steps):
+    """C4: 64 independent patient volumes (256^3, 4 time points, 31^3 Lu-177 kernel) sharded over the ranks, no collective."""
+    import torch
+
+    from pyvoxeldosimetry_b200 import KernelConvolutionCalculator
+    from pyvoxeldosimetry_b200.core import trapezoid_weights
+    from pyvoxeldosimetry_b200.engine import ConvPlan
+    from pyvoxeldosimetry_b200.multi_gpu import shard_range
+
+    wl = WORKLOADS["c4"]
+    calc = KernelConvolutionCalculator(wl["nuclide"], "water", wl["voxel"], config={"kernel_grid": wl["kgrid"], "device": str(dev)})
+    mine = shard_range(wl["volumes"], world, rank)
+    plan = ConvPlan(wl["shape"], wl["kgrid"], "reference", dev)
+    plan.set_kernel(calc._kernel_dev)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    sets = [[torch.rand(wl["shape"], device=dev, generator=g) for _ in range(wl["T"])] for _ in range(2)]  # two patients' buffers, alternated
+    w = trapezoid_weights([4.0, 24.0, 96.0, 168.0], 3600.0)
+    out = torch.empty(plan.out_shape, device=dev)
+
+    def step():
+        for v in mine:
+            plan.execute(sets[v & 1], w, None, out=out)
+
+    ms = time_steps(step, steps, 3, dev, dist)
+    plan.check_device_errors()
+    plan.close()
+    nvox = float(np.prod(wl["shape"]))
+    alg = 4.0 * (wl["T"] + 1) * nvox * wl["volumes"]
+    peak_gbs, peak_src = peaks()
+    return {"workload": wl["desc"], "scaling": "strong", "patients": wl["volumes"], "patients_per_rank": len(mine), "ms_per_job": ms,
+            "patients_per_sec": wl["volumes"] * 1e3 / ms, "voxels_per_sec": wl["volumes"] * nvox * 1e3 / ms, "gpu_launches_per_job": 5 * len(mine),
+            "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peak_gbs * world, "unit": "GB/s",
+                         "frac": round(alg / (ms * 1e-3) / 1e9 / (peak_gbs * world), 4), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
+                         "what": "algorithmic 4*(T+1) B/voxel * 64 patients / job time"}}
+
+
+def run_c5(args, dev, dist, rank, world, steps, boundary):
+    """C5: one 1024x1024x800 volume, 51^3 Y90 kernel, density-corrected.  N = 1: the whole volume on one GPU (the strong-
+    scaling anchor).  N > 1: slabs along axis 0, kernel-radius halo exchange with NCCL send/recv on a side stream, hidden
+    behind the plane-local passes of the rank's own planes; the stitched slab result is compared with a single-GPU
+    convolution of the whole volume on rank 0 (parity of the NCCL data path, inside the driver-run bench)."""
+    import torch
+
+    from pyvoxeldosimetry_b200 import KernelConvolutionCalculator
+    from pyvoxeldosimetry_b200.engine import ConvPlan
+    from pyvoxeldosimetry_b200.multi_gpu import SlabConvolver
+
+    wl = WORKLOADS["c5"]
+    shape = wl["shape"]
+    nvox = float(np.prod(shape))
+    calc = KernelConvolutionCalculator(wl["nuclide"], "water", wl["voxel"], config={"kernel_grid": wl["kgrid"], "boundary": boundary, "device": str(dev)})
+    kdev = calc._kernel_dev
+    peak_gbs, peak_src = peaks()
+    alg = 12.0 * nvox
+    res = {"workload": wl["desc"], "boundary": boundary, "scaling": "strong", "n_gpus": world}
+    # the same global volume on every rank (same seed), built plane block by plane block to bound the transient memory
+    def global_planes(lo, hi, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        full = torch.rand(shape, device=dev, generator=g)
+        return full[lo:hi].clone()
+
+    if world == 1:
+        plan = ConvPlan(shape, wl["kgrid"], boundary, dev)
+        plan.set_kernel(kdev)
+        a = global_planes(0, shape[0], 5)
+        rho = global_planes(0, shape[0], 6) + 0.5
+        out = torch.empty(plan.out_shape, device=dev)
+        ms = time_steps(lambda: plan.execute([a], None, rho, out=out), steps, 3, dev, None)
+        plan.check_device_errors()
+        res.update({"decomposition": "whole volume on one GPU", "fft_shape": list(plan.fft_shape), "gpu_launches_per_volume": 5})
+        plan.close()
+    else:
+        sc = SlabConvolver(shape, kdev, boundary, device=dev)
+        sc.interior.copy_(global_planes(sc.lo, sc.hi, 5))
+        rho = global_planes(sc.lo, sc.hi, 6) + 0.5
+        ms = time_steps(lambda: sc(density_slab=rho), steps, 3, dev, dist)
+        ms_serial = time_steps(lambda: sc(density_slab=rho, overlap=False), max(3, steps // 2), 2, dev, dist)
+        ms_compute = time_steps(lambda: sc(density_slab=rho, exchange=False), max(3, steps // 2), 2, dev, dist)
+        sc.check_device_errors()
+        halo = sc.geom["n"][0] - (sc.hi - sc.lo)
+        res.update({"decomposition": f"{world} slabs along axis 0 + NCCL halo exchange (send/recv in one group, side stream, overlapped)",
+                    "slab_planes": sc.hi - sc.lo, "halo_planes": halo, "halo_bytes_received_per_rank": int(halo * shape[1] * shape[2] * 4),
+                    "local_fft_shape": list(sc.plan.fft_shape), "ms_exchange_not_overlapped": round(ms_serial, 4),
+                    "ms_without_exchange": round(ms_compute, 4), "exchange_exposed_ms": round(ms - ms_compute, 4), "gpu_launches_per_volume": 7})
+        # parity of the NCCL data path: stitched slabs vs one whole-volume convolution on rank 0
+        mine = sc(density_slab=rho).clone()
+        pieces = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        if (shape[0] % world) == 0:
+            dist.gather(mine, pieces, dst=0)
+        if rank == 0 and pieces is not None:
+            del sc
+            torch.cuda.empty_cache()
+            plan = ConvPlan(shape, wl["kgrid"], boundary, dev)
+            plan.set_kernel(kdev)
+            whole = plan.execute([global_planes(0, shape[0], 5)], None, global_planes(0, shape[0], 6) + 0.5)
+            err = float((torch.cat(pieces) - whole).abs().max() / whole.abs().max())
+            plan.close()
+            res["slab_vs_whole_volume_max_err_of_peak"] = err
+            res["parity_ok"] = bool(err <= 1e-5)
+    res.update({"ms_per_volume": ms, "volumes_per_sec": 1e3 / ms, "voxels_per_sec": nvox * 1e3 / ms,
+                "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peak_gbs * world, "unit": "GB/s",
+                             "frac": round(alg / (ms * 1e-3) / 1e9 / (peak_gbs * world), 4), "traffic": None,
+                             "peak_source": peak_src + f" x {world} GPUs", "what": "algorithmic 12 B/voxel / time per volume"}})
+    return res
+
+
+def dram_traffic_for(build_id: str, workload: str, boundary: str):
+    """dram__bytes_read + write of the whole path from the committed ncu --set full capture - only when the capture was
+    taken from THIS build of the kernels (the file carries the library's build id)."""
+    p = os.path.join(REPO, "profiles", "r02_dram_traffic_c3.json")
+    if workload != "c3" or boundary != "reference" or not os.path.exists(p):
+        return None, "no capture for this workload"
+    d = json.load(open(p))
+    if d.get("build_id") != build_id:
+        return None, f"stale: capture is of build {d.get('build_id')}, library is {build_id}"
+    return d.get("_whole_path_dram_bytes"), os.path.basename(p)
+
+
 def run_ours(args, wl):
     import torch
 
@@ -352,7 +583,7 @@ def run_ours(args, wl):
     dist = None
     full_affinity = os.sched_getaffinity(0)
     # host threads (and so the pinned staging buffers of the e2e leg, first touch) on the GPU's own NUMA node
-    sys.stderr.write(bind_to_gpu_numa(local) + "\n")
+    sys.stderr.write(bind_to_gpu_numa(local, int(os.environ.get("LOCAL_WORLD_SIZE", world))) + "\n")
     if world > 1:
         import torch.distributed as dist_mod
 
@@ -419,209 +650,136 @@ def run_ours(args, wl):
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    plan.check_device_errors()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * 1e3 / ms_step  # volumes/s, whole job
+    info = plan.info
+    build_id = plan.lib.build_id()
 
-    # ---- e2e through the public calculator API with pinned host buffers
-    pin_acts = [torch.from_numpy(a).pin_memory() for a in acts_h]
-    pin_rho = None if rho_h is None else torch.from_numpy(rho_h).pin_memory()
-    pin_out = torch.empty(plan.out_shape, dtype=torch.float32).pin_memory()
-    vox = (wl["voxel"],) * 3
+    # ---- e2e through the reference-facing API with HOST buffers
+    del acts, rho, out
+    e2e = measure_e2e(wl, args, calc, plan, acts_h, rho_h, dev, dist, world, barrier)
+    plan.close()
+    calc._plans.clear()
+    torch.cuda.empty_cache()
 
-    def e2e_step():
-        if wl["T"] == 1:
-            return calc.calculate_dose_rate(pin_acts[0], vox, tissue_densities=pin_rho, out=pin_out)
-        return calc.calculate_absorbed_dose(pin_acts, times, vox, tissue_densities=pin_rho, out=pin_out)
-
-    e2e_steps = max(3, min(args.steps, 10))
-    e2e_variants = {}
-    h2d_den_bytes = pin_rho.numel() * 4 if pin_rho is not None else 0
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize(dev)
-    dt_single = (time.perf_counter() - t0) / e2e_steps  # one blocking call per volume
-    dt, e2e_api = dt_single, "KernelConvolutionCalculator.calculate_dose_rate(host ndarray, tissue_densities=host ndarray, out=pinned)"
-    if wl["T"] == 1:
-        # pipelined batch call: every volume still pays its own H2D (activity + density) and D2H, but copies in
-        # both directions and the convolution overlap across consecutive volumes (three streams, double buffers)
-        pin_out2 = torch.empty(plan.out_shape, dtype=torch.float32).pin_memory()
-        nb = max(8, e2e_steps)
-        batch_acts = [pin_acts[0]] * nb
-        batch_den = None if pin_rho is None else [pin_rho] * nb
-        batch_outs = [pin_out if i % 2 == 0 else pin_out2 for i in range(nb)]
-        calc.calculate_dose_rate_batch(batch_acts[:3], vox, None if batch_den is None else batch_den[:3], batch_outs[:3])
-        barrier()
-        t0 = time.perf_counter()
-        calc.calculate_dose_rate_batch(batch_acts, vox, batch_den, batch_outs)
-        torch.cuda.synchronize(dev)
-        dt_batch = (time.perf_counter() - t0) / nb
-        if dt_batch < dt:
-            dt, e2e_api = dt_batch, f"KernelConvolutionCalculator.calculate_dose_rate_batch({nb} host volumes + {nb} host density volumes -> {nb} host dose maps), pipelined H2D/compute/D2H"
-        e2e_variants["batch_float_density_ms"] = dt_batch * 1e3
-        if pin_rho is not None:
-            # the CT as scanners store it: int16 Hounsfield units (2 bytes per voxel over the link), turned into the same
-            # densities on the device (HU -1000 / -700 / 32 / 350 <-> 0.00129 / 0.26 / 1.04 / 1.42 g/cm3 through tissue.HU_KNOTS)
-            hu_h = np.full(wl["shape"], -1000, dtype=np.int16)
-            hu_h[rho_h > 0.2] = -700
-            hu_h[rho_h > 1.0] = 32
-            hu_h[rho_h > 1.4] = 350
-            pin_hu = torch.from_numpy(hu_h).pin_memory()
-            calc.calculate_dose_rate_batch(batch_acts[:3], vox, None, batch_outs[:3], ct_hu=[pin_hu] * 3)
-            barrier()
-            t0 = time.perf_counter()
-            calc.calculate_dose_rate_batch(batch_acts, vox, None, batch_outs, ct_hu=[pin_hu] * nb)
-            torch.cuda.synchronize(dev)
-            dt_ct = (time.perf_counter() - t0) / nb
-            e2e_variants["batch_int16_ct_ms"] = dt_ct * 1e3
-            if dt_ct < dt:
-                dt, e2e_api = dt_ct, f"KernelConvolutionCalculator.calculate_dose_rate_batch({nb} host activity volumes (float32) + {nb} host CT volumes (int16 HU, density derived on the device) -> {nb} host dose maps), pipelined H2D/compute/D2H"
-                h2d_den_bytes = pin_hu.numel() * 2
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world / float(t.item())
-    h2d = int(sum(a.numel() for a in pin_acts) * 4 + h2d_den_bytes)
-    d2h = int(pin_out.numel() * 4)
+    # ---- the other named configurations, inside the same line (driver-visible): C4 (sharded patients), C5 (slabs + NCCL)
+    extras = {}
+    if args.workload == "c3" and not args.no_extras:
+        xs = max(3, min(args.steps, 10))
+        try:
+            extras["c4"] = run_c4(args, dev, dist, rank, world, xs)
+            torch.cuda.empty_cache()
+            for b in ("same", "reference"):
+                extras["c5_" + b] = run_c5(args, dev, dist, rank, world, xs, b)
+                torch.cuda.empty_cache()
+        except Exception as e:  # an extra must never cost the headline line
+            extras["error"] = f"{type(e).__name__}: {e}"[:400]
 
     if rank == 0:
         alg_bytes = 4.0 * (wl["T"] + 1 + (1 if wl["density"] else 0)) * nvox
-        info = plan.info
         kernels = [{"name": n, "ms": round(ms, 4), "hbm_bytes": b, "gbs": round(b / ms / 1e6, 1) if ms > 0 else None,
                     "frac_of_peak": round(b / ms / 1e6 / peak_gbs, 3) if ms > 0 else None} for (n, ms, b) in (acc or [])]
         ksum = sum(k["ms"] for k in kernels) or ms_step
         dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
-        traffic = None  # dram__bytes_read+write of the whole path from the committed ncu --set full capture (same workload only)
-        tpath = os.path.join(REPO, "profiles", "r01h_dram_traffic_c3.json")
-        if args.workload == "c3" and args.boundary == "reference" and os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("_whole_path_dram_bytes")
+        traffic, traffic_src = dram_traffic_for(build_id, args.workload, args.boundary)
         line = {
             "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox,
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "boundary": args.boundary, "fft_shape": list(plan.fft_shape),
-                       "volumes_per_step_per_gpu": 1, "l2": "inputs (>=419 MB per volume for c3) exceed the 126 MB L2",
-                       "parallelism": f"independent volumes sharded over {world} rank(s), no data-path collective"},
+            "config": {"workload": wl["desc"], "boundary": args.boundary, "fft_shape": list(info.m),
+                       "volumes_per_step_per_gpu": 1, "l2": f"inputs + work buffer ({info.workspace_bytes / 2e6:.0f} MB per pass) exceed the 126 MB L2"
+                       if info.workspace_bytes > 4e8 else "small workload: L2-resident (launch-bound), not flushed",
+                       "parallelism": f"independent volumes sharded over {world} rank(s), no data-path collective", "library_build_id": build_id},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
-                         "frac": round(achieved / peak_gbs, 4), "traffic": traffic,
+                         "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "traffic_source": traffic_src,
                          "what": "whole conv path (all launches of one volume): algorithmic 4*(T+1+[density]) B/voxel / time per volume",
                          "peak_source": peak_src, "algorithmic_bytes_per_volume": alg_bytes,
                          "implementation_bytes_per_volume": info.hbm_bytes_per_execute,
                          "implementation_gbs": round(info.hbm_bytes_per_execute / (ms_step * 1e-3) / 1e9, 1),
                          "dominant_kernel": dom, "dominant_share_of_step": round(dom["ms"] / ksum, 3) if dom else None},
             "kernels": kernels,
-            "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": dt * 1e3, "single_call_ms": dt_single * 1e3, "api": e2e_api, "variants_ms": e2e_variants},
+            "e2e": e2e,
+            "extras": extras,
             "gpu_launches": int(info.passes) * args.steps,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import dose_oracle as orc
-
             os.sched_setaffinity(0, full_affinity)  # the CPU leg may use every host core again
-
-            k64 = calc.kernel.astype(np.float32).astype(np.float64)
-            rate, sample, secs = cpu_reference_time(wl, 20.0, acts_h, rho_h, k64)
-            line["cpu_baseline"] = {"value": rate / nvox, "unit": "volumes/s", "cores": 1, "kind": "port",
-                                    "sample": sample + f" ({secs:.1f} s); np.fft is single-threaded", "host_cores_available": os.cpu_count()}
-            try:
-                pick = tuple(int(x) for x in sample.split(" on a ")[1].split(" ")[0].split("x"))
-                tv, tc = cpu_threaded_time(wl, acts_h, rho_h, k64, pick)
-                line["cpu_baseline"]["threaded"] = {"value": tv, "unit": "volumes/s", "cores": tc,
-                                                    "what": "same mathematics via scipy.fft rfftn/irfftn, workers = all host threads, same sample"}
-            except Exception as e:  # pragma: no cover
-                line["cpu_baseline"]["threaded"] = {"unavailable": str(e)[:200]}
+            line["cpu_baseline"] = cpu_baseline_leg(wl, acts_h, times, rho_h)
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def cpu_baseline_leg(wl, acts_h, times, rho_h):
+    """The reference's CPU path beside the GPU number, same run, same box, same inputs (float64): the reference's own class
+    from oracle/_ref on the FULL volume, 1 warm-up + best of 3 (BASELINE.md section 4 A), single-threaded by construction;
+    plus the same mathematics on every host thread (scipy.fft - not the reference's code)."""
+    from oracle import dose_oracle as orc
+
+    nvox = float(np.prod(wl["shape"]))
+    maps64 = [a.astype(np.float64) for a in acts_h]
+    vox = (float(wl["voxel"]),) * 3
+    try:
+        calc, k64 = load_reference_calculator(wl)
+        kind, what = "reference", "KernelConvolutionCalculator of oracle/_ref (byte-identical copy of the reference)"
+        step = lambda: reference_step_real(calc, maps64, times, vox, rho_h)
+    except Exception as e:
+        sys.stderr.write(f"[bench] reference package unavailable ({e}); timing the oracle port\n")
+        k64 = orc.make_kernel(wl["nuclide"], wl["voxel"], wl["kgrid"]).astype(np.float32).astype(np.float64)
+        kind, what = "port", "oracle.conv_reference (literal np.fft expression of core/kernel_convolution.py:71-74)"
+        step = lambda: reference_step(maps64, k64, rho_h)
+    step()  # warm-up
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out = {"value": 1.0 / best, "unit": "volumes/s", "cores": 1, "kind": kind, "seconds_per_volume": round(best, 3),
+           "sample": f"{what}, float64, the full {'x'.join(map(str, wl['shape']))} volume, 1 warm-up + best of 3; np.fft is single-threaded",
+           "host_cores_available": os.cpu_count()}
+    try:
+        tv, tc = cpu_threaded_time(wl, acts_h, rho_h, k64, tuple(wl["shape"]))
+        out["threaded"] = {"value": tv, "unit": "volumes/s", "cores": tc,
+                           "what": "same mathematics via scipy.fft rfftn/irfftn, workers = all host threads, full volume, best of 2 (context only)"}
+    except Exception as e:  # pragma: no cover
+        out["threaded"] = {"unavailable": str(e)[:200]}
+    return out
+
+
 def run_sharded(args, wl, name):
-    """C4 / C5: a fixed job shared by the ranks (strong scaling).  C4 shards independent volumes (no collective);
-    C5 splits one volume into slabs and exchanges kernel-radius halos between neighbours with NCCL send/recv."""
+    """`--workload c4|c5` on their own (the default c3 run carries both in `extras`)."""
     import torch
 
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    import torch.distributed as dist
-
+    dist = None
     if world > 1:
+        import torch.distributed as dist
+
         dist.init_process_group(backend="nccl", device_id=dev)
-    else:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group(backend="nccl", rank=0, world_size=1, device_id=dev)
-    from pyvoxeldosimetry_b200 import KernelConvolutionCalculator
-    from pyvoxeldosimetry_b200.engine import ConvPlan
-    from pyvoxeldosimetry_b200.multi_gpu import SlabConvolver, shard_range
-
-    boundary = args.boundary
-    calc = KernelConvolutionCalculator(wl["nuclide"], "water", wl["voxel"], config={"kernel_grid": wl["kgrid"], "boundary": boundary, "device": str(dev)})
-    kdev = calc._kernel_dev
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    if name == "c4":
-        from pyvoxeldosimetry_b200.core import trapezoid_weights
-
-        mine = shard_range(wl["volumes"], world, rank)
-        plan = ConvPlan(wl["shape"], wl["kgrid"], boundary, dev)
-        plan.set_kernel(kdev)
-        sets = [[torch.rand(wl["shape"], device=dev, generator=g) for _ in range(wl["T"])] for _ in range(2)]  # two patients' buffers, alternated
-        w = trapezoid_weights([4.0, 24.0, 96.0, 168.0], 3600.0)
-        out = torch.empty(plan.out_shape, device=dev)
-
-        def step():
-            for v in mine:
-                plan.execute(sets[v & 1], w, None, out=out)
-        units, extra, launches = wl["volumes"], {"volumes_per_rank": len(mine), "fft_shape": list(plan.fft_shape)}, 5 * len(mine)
-    else:
-        sc = SlabConvolver(wl["shape"], kdev, boundary, device=dev)
-        local_in = torch.rand((sc.hi - sc.lo,) + tuple(wl["shape"][1:]), device=dev, generator=g)
-        rho = torch.rand((sc.hi - sc.lo,) + tuple(wl["shape"][1:]), device=dev, generator=g) + 0.5
-
-        def step():
-            sc(local_in, rho)
-        units, launches = 1, 5
-        extra = {"slab_planes": sc.hi - sc.lo, "halo_planes": sc.geom["n"][0] - (sc.hi - sc.lo), "local_fft_shape": list(sc.plan.fft_shape)}
-    for _ in range(max(3, args.warmup)):
-        step()
-    torch.cuda.synchronize(dev)
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    xs = max(3, args.steps)
+    r = run_c4(args, dev, dist, rank, world, xs) if name == "c4" else run_c5(args, dev, dist, rank, world, xs, args.boundary)
     if rank == 0:
         nvox = float(np.prod(wl["shape"]))
-        value = units * 1e3 / ms_step
-        alg = 4.0 * (wl["T"] + 1 + (1 if wl["density"] else 0)) * nvox * units
-        peak_gbs, peak_src = peaks()
-        emit({
-            "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox, "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict({"workload": wl["desc"], "boundary": boundary, "l2": "inputs exceed the 126 MB L2"}, **extra),
-            "roofline": {"bound": "hbm", "achieved": round(alg / (ms_step * 1e-3) / 1e9, 1), "peak": peak_gbs * world, "unit": "GB/s",
-                         "frac": round(alg / (ms_step * 1e-3) / 1e9 / (peak_gbs * world), 4), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
-            "gpu_launches": launches * args.steps,
-        })
-    dist.barrier()
-    dist.destroy_process_group()
+        ms = r.get("ms_per_job", r.get("ms_per_volume"))
+        units = wl.get("volumes", 1)
+        emit({"metric": "dose_volumes_per_sec", "value": units * 1e3 / ms, "unit": "volumes/s", "voxels_per_sec": units * nvox * 1e3 / ms,
+              "n_gpus": world, "steps": xs, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"], "boundary": args.boundary, "l2": "inputs exceed the 126 MB L2"},
+              "roofline": r["roofline"], "detail": r, "gpu_launches": r.get("gpu_launches_per_job", r.get("gpu_launches_per_volume", 5)) * xs})
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -634,6 +792,7 @@ def main():
     ap.add_argument("--boundary", default=None, choices=["reference", "same"],
                     help="default: reference (the reference's circular semantics); c5 defaults to same (zero boundary)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C4 / C5 legs of the default c3 run")
     args = ap.parse_args()
     if args.boundary is None:
         args.boundary = "same" if args.workload == "c5" else "reference"

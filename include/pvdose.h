@@ -124,6 +124,13 @@ int pvd_conv_execute(pvd_plan* plan, const float* const* h_act, const float* h_w
 int pvd_conv_forward_planes(pvd_plan* plan, const float* const* h_act, const float* h_weights, int T, float gain,
                             int plane_lo, int plane_hi, void* stream);
 int pvd_conv_finish(pvd_plan* plan, const float* density, float rho_min, float rho_cut, float* dose, void* stream);
+/* pvd_conv_finish in two steps: the passes between the plane-local ones (x forward * spectrum * x inverse, y inverse), then
+ * the plane-local output pass (z complex-to-real, crop, density epilogue) of OUTPUT planes [plane_lo, plane_hi) - so that an
+ * end-to-end caller can feed the density map plane block by plane block while earlier blocks of the dose map already
+ * travel back to the host (the link is full duplex).  density / dose point at plane 0 of the full volumes. */
+int pvd_conv_middle(pvd_plan* plan, void* stream);
+int pvd_conv_output_planes(pvd_plan* plan, const float* density, float rho_min, float rho_cut, float* dose, int plane_lo,
+                           int plane_hi, void* stream);
 
 int pvd_plan_destroy(pvd_plan* plan);
 

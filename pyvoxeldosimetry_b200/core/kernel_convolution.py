@@ -190,6 +190,102 @@ class KernelConvolutionCalculator(DosimetryCalculator):
                             float(cfg.get("rho_cut", 0.0)), float(cfg.get("scale", 1.0)))
         return dose
 
+    HOST_PIPELINE_CHUNKS = 8
+
+    def _host_call(self, maps: Sequence, weights: Optional[Sequence[float]], voxel_size, tissue_densities=None, out=None, ct_hu=None,
+                   rescale=None):
+        """Host arrays in -> host array out (the reference's calling convention, core/kernel_convolution.py:48-76).
+        CUDA tensors in -> CUDA tensor out, no copies.
+
+        The host form is a pipeline over the link, which is what an end-to-end call costs (the convolution itself is
+        ~1 ms of a ~20 ms call): the activity goes up through the staging engine and the forward passes and the x / y
+        inverse passes run; then, plane block by plane block, the density (or int16 CT) block goes up on one stream, the
+        output pass of that block runs, and the finished dose block goes down on a third stream straight into pinned
+        memory - upload of block i+1 and download of block i use the two directions of the link at the same time."""
+        if len(maps) == 0:
+            raise ValueError("No activity maps provided")
+        on_device = isinstance(maps[0], torch.Tensor) and maps[0].is_cuda
+        den_src = tissue_densities if tissue_densities is not None else ct_hu
+        host_den = den_src is None or isinstance(den_src, np.ndarray)
+        if on_device or not host_den:
+            dose = self._convolve(maps, weights, voxel_size, tissue_densities, ct_hu=ct_hu, rescale=rescale)
+            return dose if on_device else self._to_host(dose, out)
+        shape = tuple(maps[0].shape)
+        if len(shape) != 3:
+            raise ValueError("activity maps must be 3-D")
+        if any(tuple(m.shape) != shape for m in maps):
+            raise ValueError("All activity maps must have the same dimensions")
+        if tissue_densities is not None and ct_hu is not None:
+            raise ValueError("give tissue_densities or ct_hu, not both")
+        kdev, tag = self._kernel_for(voxel_size)
+        plan = self._plans.get(shape, tuple(kdev.shape), self.boundary, self.device, tag, lambda: kdev, self.algo)
+        self._last_plan = plan
+        want64 = str(self.config.get("output_dtype", "float32")) == "float64"
+        pinned_result = out is None and not want64
+        if plan.info.algo != engine._capi.ALGO_FFT or len(maps) > engine.MAX_T or int(np.prod(shape)) * 4 < (8 << 20):
+            dose = self._convolve(maps, weights, voxel_size, tissue_densities, ct_hu=ct_hu, rescale=rescale)
+            return self._to_host(dose, out)
+        if den_src is not None and tuple(den_src.shape) != plan.out_shape:
+            raise ValueError(("tissue_densities" if tissue_densities is not None else "ct_hu") + " must have the shape of the activity map")
+        cfg, dev, lib, h = self.config, self.device, plan.lib, plan.handle
+        rho_ref, rho_min, rho_cut, scale = (float(cfg.get("rho_ref", 1.0)), float(cfg.get("rho_min", 0.1)), float(cfg.get("rho_cut", 0.0)),
+                                            float(cfg.get("scale", 1.0)))
+        gain = scale * (rho_ref if den_src is not None else 1.0)
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            acts = [self._activity_to_device(m, rescale) for m in maps]
+            w = None if weights is None else [float(x) for x in weights]
+            lib.conv_forward_planes(h, [a.data_ptr() for a in acts], w, gain, 0, shape[0], main.cuda_stream)
+            lib.conv_middle(h, main.cuda_stream)
+            O0 = plan.out_shape[0]
+            d_out = torch.empty(plan.out_shape, dtype=torch.float32, device=dev)
+            d_den = None
+            if den_src is not None:
+                den_arr = np.ascontiguousarray(den_src)
+                is_hu = ct_hu is not None
+                if den_arr.dtype not in (np.float32, np.float64, np.int16):
+                    den_arr = den_arr.astype(np.float32)
+                d_den = torch.empty(plan.out_shape, dtype=torch.float32, device=dev)
+                d_hu = torch.empty(plan.out_shape, dtype=torch.int16, device=dev) if (is_hu and den_arr.dtype == np.int16) else None
+                if is_hu:
+                    from ..tissue.density import HU_KNOTS
+
+                    knots = cfg.get("hu_knots", HU_KNOTS)
+            host = torch.empty(plan.out_shape, dtype=torch.float32, pin_memory=True) if pinned_result else None
+            if not hasattr(self, "_side"):
+                self._side = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_in, s_out = self._side
+            s_in.wait_stream(main)
+            s_out.wait_stream(main)
+            stager = engine.HostStager.get(dev)
+            nch = min(self.HOST_PIPELINE_CHUNKS, O0)
+            bounds = [O0 * i // nch for i in range(nch + 1)]
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                if d_den is not None:
+                    with torch.cuda.stream(s_in):
+                        if d_hu is not None:
+                            stager.upload(den_arr[lo:hi], out=d_hu[lo:hi])
+                            lib.hu_to_density(d_hu[lo:hi].data_ptr(), True, knots, d_den[lo:hi].data_ptr(), d_den[lo:hi].numel(), s_in.cuda_stream)
+                        else:
+                            stager.upload(den_arr[lo:hi], out=d_den[lo:hi])
+                            if is_hu:
+                                lib.hu_to_density(d_den[lo:hi].data_ptr(), False, knots, d_den[lo:hi].data_ptr(), d_den[lo:hi].numel(), s_in.cuda_stream)
+                    main.wait_stream(s_in)
+                lib.conv_output_planes(h, None if d_den is None else d_den.data_ptr(), rho_min, rho_cut, d_out.data_ptr(), lo, hi, main.cuda_stream)
+                if host is not None:
+                    s_out.wait_stream(main)
+                    with torch.cuda.stream(s_out):
+                        host[lo:hi].copy_(d_out[lo:hi], non_blocking=True)
+            if host is not None:
+                s_out.synchronize()
+                main.wait_stream(s_out)
+                res = host.numpy()
+            else:
+                res = engine.to_host(d_out, out, want64)
+            main.synchronize()  # every tensor of this call is idle before the allocator may hand it out again
+        self._check_device_errors()
+        return out if (out is not None and not isinstance(out, torch.Tensor)) else res
+
     def _to_host(self, dose: torch.Tensor, out=None) -> np.ndarray:
         want64 = str(self.config.get("output_dtype", "float32")) == "float64"
         host = engine.to_host(dose, out, want64)
@@ -210,10 +306,7 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         """A1.  Host ndarray in -> host ndarray out; CUDA tensor in -> CUDA tensor out (no copies).
         Density correction (A9): `tissue_densities` (g/cm3) or `ct_hu` (the CT in Hounsfield units, int16 or float).
         `activity_map` may be float64 / float32, or int16 / uint16 stored values with `rescale` = (slope, intercept)."""
-        dose = self._convolve([activity_map], None, voxel_size, tissue_densities, ct_hu=ct_hu, rescale=rescale)
-        if isinstance(activity_map, torch.Tensor) and activity_map.is_cuda:
-            return dose
-        return self._to_host(dose, out)
+        return self._host_call([activity_map], None, voxel_size, tissue_densities, out, ct_hu, rescale)
 
     def calculate_dose_rate_batch(self, activity_maps: Sequence, voxel_size=None, tissue_densities=None,
                                   outs: Optional[Sequence] = None, ct_hu=None, rescale=None) -> list:
@@ -350,10 +443,7 @@ class KernelConvolutionCalculator(DosimetryCalculator):
         if len(activity_maps) != len(time_points):
             raise ValueError("Number of activity maps must match number of time points")
         w = trapezoid_weights(time_points, HOURS_TO_SECONDS)
-        dose = self._convolve(list(activity_maps), w, voxel_size, tissue_densities, ct_hu=ct_hu)
-        if isinstance(activity_maps[0], torch.Tensor) and activity_maps[0].is_cuda:
-            return dose
-        return self._to_host(dose, out)
+        return self._host_call(list(activity_maps), w, voxel_size, tissue_densities, out, ct_hu)
 
     def calculate_absorbed_dose_from_accumulated(self, accumulated_activity, voxel_size=None, tissue_densities=None, out=None):
         """Called by the reference front door (core/dose_calculator.py:104,123) but defined nowhere there;
@@ -362,10 +452,7 @@ class KernelConvolutionCalculator(DosimetryCalculator):
 
     def calculate_weighted(self, activity_maps, weights: Sequence[float], voxel_size=None, tissue_densities=None, out=None):
         """conv(sum_i w_i a_i, k) for caller-chosen weights (used by DoseCalculator's activity mode)."""
-        dose = self._convolve(list(activity_maps), [float(x) for x in weights], voxel_size, tissue_densities)
-        if isinstance(activity_maps[0], torch.Tensor) and activity_maps[0].is_cuda:
-            return dose
-        return self._to_host(dose, out)
+        return self._host_call(list(activity_maps), [float(x) for x in weights], voxel_size, tissue_densities, out)
 
     def _resample_activity(self, activity_map, input_voxel_size, output_voxel_size):
         """The reference stub returns None (kernel_convolution.py:108-115).  Not needed here: the kernel is

@@ -821,6 +821,8 @@ int conv_forward(pvd_plan* p, const float* const* h_act, const float* h_weights,
 }
 
 int conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, cudaStream_t stream, bool mark);
+int conv_middle(pvd_plan* p, cudaStream_t stream, bool mark);
+int conv_output(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, int lo, int hi, cudaStream_t stream, bool mark);
 
 int check_execute_state(pvd_plan* p, const float* const* h_act, int T) {
     if (T < 1 || T > PVD_MAX_T) return fail(PVD_ERR_INVALID, "T=%d outside [1,%d]: pre-accumulate with pvd_weighted_sum", T, PVD_MAX_T);
@@ -863,37 +865,65 @@ int pvd_conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_
     return conv_finish(p, density, rho_min, rho_cut, dose, (cudaStream_t)stream_, false);
 }
 
+int pvd_conv_middle(pvd_plan* p, void* stream_) {
+    if (!p) return fail(PVD_ERR_INVALID, "null argument");
+    if (!p->ws) return fail(PVD_ERR_STATE, "workspace not set");
+    if (!p->kernel_set) return fail(PVD_ERR_STATE, "dose kernel not set");
+    if (p->algo != PVD_ALGO_FFT) return fail(PVD_ERR_UNSUPPORTED, "the split form exists for the FFT algorithm only");
+    return conv_middle(p, (cudaStream_t)stream_, false);
+}
+
+int pvd_conv_output_planes(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, int plane_lo, int plane_hi,
+                           void* stream_) {
+    if (!p || !dose) return fail(PVD_ERR_INVALID, "null argument");
+    if (!p->ws) return fail(PVD_ERR_STATE, "workspace not set");
+    if (p->algo != PVD_ALGO_FFT) return fail(PVD_ERR_UNSUPPORTED, "the split form exists for the FFT algorithm only");
+    if (plane_lo < 0 || plane_hi > p->on[0] || plane_lo > plane_hi)
+        return fail(PVD_ERR_INVALID, "output plane range [%d, %d) outside [0, %d)", plane_lo, plane_hi, p->on[0]);
+    return conv_output(p, density, rho_min, rho_cut, dose, plane_lo, plane_hi, (cudaStream_t)stream_, false);
+}
+
 namespace {
 
-int conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, cudaStream_t stream, bool mark) {
+// P3 (x forward * cached spectrum * x inverse) and P4 (y inverse): everything between the plane-local passes.
+int conv_middle(pvd_plan* p, cudaStream_t stream, bool mark) {
     const double c = 8.0 * p->Nh;
-    const float rho_ref = 1.f, scale = 1.f;  // folded into the input weights by conv_forward
-    int rc;
     if (mark) p->mark(stream, "P3 cols x forward*spectrum*inverse", c * p->m[1] * ((double)p->n[0] + p->m[0] + p->on[0]));
-    rc = launch_cols(p, 0, COL_CONV, p->buf(), p->buf(), 0, p->m[1], p->n[0], p->olo[0], p->on[0], 1.f, stream);
+    int rc = launch_cols(p, 0, COL_CONV, p->buf(), p->buf(), 0, p->m[1], p->n[0], p->olo[0], p->on[0], 1.f, stream);
     if (rc) return rc;
     if (mark) p->mark(stream, "P4 cols y inverse", c * p->on[0] * ((double)p->m[1] + p->on[1]));
-    rc = launch_cols(p, 1, COL_INV, p->buf(), p->buf(), p->olo[0], p->on[0], p->m[1], p->olo[1], p->on[1], 1.f, stream);
-    if (rc) return rc;
+    return launch_cols(p, 1, COL_INV, p->buf(), p->buf(), p->olo[0], p->on[0], p->m[1], p->olo[1], p->on[1], 1.f, stream);
+}
+
+// P5 (z complex-to-real, crop, density epilogue) of OUTPUT planes [lo, hi); density / dose point at plane 0 of the full volumes.
+int conv_output(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, int lo, int hi, cudaStream_t stream,
+                bool mark) {
+    const double c = 8.0 * p->Nh;
+    const float rho_ref = 1.f, scale = 1.f;  // folded into the input weights by conv_forward
+    const int O0 = hi - lo;
     if (mark) p->mark(stream, "P5 rows_inv (z C2R + density + crop)",
-                      c * p->on[0] * p->on[1] + (density ? 8.0 : 4.0) * p->on[0] * p->on[1] * p->on[2]);
+                      c * O0 * p->on[1] + (density ? 8.0 : 4.0) * O0 * p->on[1] * p->on[2]);
     RowInvArgs a;
     memset(&a, 0, sizeof a);
-    a.in = p->buf();
     a.in_s0 = (long long)p->m[1] * p->Sz;
     a.in_s1 = p->Sz;
-    a.x_lo = p->olo[0];
+    const int xoff = p->olo[0] + lo;  // first transform plane of this range: folded into the base pointer
+    float2* const in_base = p->buf() + (long long)xoff * a.in_s0;
+    a.in = in_base;
+    a.x_lo = 0;
     a.y_lo = p->olo[1];
     a.z_lo = p->olo[2];
-    a.O0 = p->on[0];
+    a.O0 = O0;
     a.O1 = p->on[1];
     a.O2 = p->on[2];
-    a.out = dose;
     a.out_s0 = (long long)p->on[1] * p->on[2];
     a.out_s1 = p->on[2];
-    a.density = density;
+    a.out = dose + (long long)lo * a.out_s0;
     a.den_s0 = a.out_s0;
     a.den_s1 = a.out_s1;
+    a.density = density ? density + (long long)lo * a.den_s0 : nullptr;
+    density = a.density;
+    dose = a.out;
     a.rho_ref = rho_ref;
     a.rho_min = rho_min;
     a.rho_cut = rho_cut;
@@ -913,8 +943,9 @@ int conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut,
               (!density || (((uintptr_t)density & 15) == 0 && a.den_s0 % 4 == 0 && a.den_s1 % 4 == 0)))
                  ? 1
                  : 0;
-    const long long nrows = (long long)p->on[0] * p->on[1];
+    const long long nrows = (long long)O0 * p->on[1];
     const long long per = 2LL << p->rowLlog;
+    if (nrows <= 0) return PVD_OK;
     if (p->fastRows && p->usePipe && p->rowPipeGrid[1] > 0 && nrows < 2000000000LL) {
         const FastRows* f = p->fastRows;
         const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[1]);
@@ -930,15 +961,15 @@ int conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut,
                 const cuuint64_t gdim[2] = {(cuuint64_t)p->Sz, (cuuint64_t)nrows};
                 const cuuint64_t gstr[1] = {(cuuint64_t)a.in_s1 * 8};
                 const cuuint32_t box[2] = {(cuuint32_t)lsc, 32};
-                if (get_encode_tiled()(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, p->buf(), gdim, gstr, box, estr,
+                if (get_encode_tiled()(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, in_base, gdim, gstr, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
                     a.use_tma = 1;
             } else {  // cropped output (x_lo / y_lo, M1 > O1): a tile never straddles x because 32 divides O1
-                const cuuint64_t gdim[3] = {(cuuint64_t)p->Sz, (cuuint64_t)p->m[1], (cuuint64_t)p->m[0]};
+                const cuuint64_t gdim[3] = {(cuuint64_t)p->Sz, (cuuint64_t)p->m[1], (cuuint64_t)(p->m[0] - xoff)};
                 const cuuint64_t gstr[2] = {(cuuint64_t)a.in_s1 * 8, (cuuint64_t)a.in_s0 * 8};
                 const cuuint32_t box[3] = {(cuuint32_t)lsc, 32, 1};
-                if (get_encode_tiled()(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p->buf(), gdim, gstr, box, estr,
+                if (get_encode_tiled()(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, in_base, gdim, gstr, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
                     a.use_tma = 1;
@@ -973,6 +1004,11 @@ int conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut,
     PVD_CUDA_CHECK("rows_inv_kernel");
     if (mark) p->mark_end(stream);
     return PVD_OK;
+}
+
+int conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_cut, float* dose, cudaStream_t stream, bool mark) {
+    if (int rc = conv_middle(p, stream, mark)) return rc;
+    return conv_output(p, density, rho_min, rho_cut, dose, 0, p->on[0], stream, mark);
 }
 
 }  // namespace

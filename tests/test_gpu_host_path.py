@@ -140,3 +140,43 @@ def test_user_kernel_survives_other_voxel_size_and_getter_is_read_only():
         calc.kernel[3, 3, 3] = 0.0  # in-place edits would never reach the device
     k[3, 3, 3] = 123.0  # the caller's array is not aliased
     assert calc.kernel[3, 3, 3] != 123.0
+
+
+@pytest.mark.parametrize("boundary", ["reference", "same"])
+def test_host_pipeline_density_blocks_and_dose_blocks_overlap_correctly(boundary):
+    """Volumes above 8 MB take the pipelined host call (density / CT uploaded plane block by plane block while finished
+    dose blocks travel back): every input flavour must give the oracle's dose map."""
+    from pyvoxeldosimetry_b200.tissue.density import HU_KNOTS
+
+    rng = np.random.default_rng(15)
+    shape = (150, 144, 120)  # 10.4 MB per float32 volume; 150 planes do not divide by the 8 blocks
+    a = rng.uniform(0, 1e3, shape).astype(np.float32)
+    a[60:90, 50:100, 40:80] = 2e6
+    rho = rng.choice(np.array([0.00129, 0.26, 1.04, 1.42], dtype=np.float32), size=shape)
+    hu = rng.choice(np.array([-1000, -700, 32, 350], dtype=np.int16), size=shape)
+    calc = _calc(boundary=boundary)
+    k = calc.kernel.astype(np.float32).astype(np.float64)
+    conv = (orc.conv_reference_fast if boundary == "reference" else (lambda x, kk: orc.conv_same(x, kk, fast=True)))(a.astype(np.float64), k)
+    ref_plain = conv
+    ref_rho = orc.density_correct(conv, rho.astype(np.float64), 1.0, 0.1, 0.0)
+    ref_hu = orc.density_correct(conv, orc.hu_to_density(hu.astype(np.float64), np.asarray(HU_KNOTS, dtype=np.float64)), 1.0, 0.1, 0.0)
+    vs = (1.0, 1.0, 1.0)
+    assert orc.rel_err_of_peak(calc.calculate_dose_rate(a, vs), ref_plain) <= 1e-4
+    assert orc.rel_err_of_peak(calc.calculate_dose_rate(a.astype(np.float64), vs, tissue_densities=rho), ref_rho) <= 1e-4
+    assert orc.rel_err_of_peak(calc.calculate_dose_rate(a, vs, tissue_densities=rho.astype(np.float64)), ref_rho) <= 1e-4
+    assert orc.rel_err_of_peak(calc.calculate_dose_rate(a, vs, ct_hu=hu), ref_hu) <= 1e-4
+    assert orc.rel_err_of_peak(calc.calculate_dose_rate(a, vs, ct_hu=hu.astype(np.float32)), ref_hu) <= 1e-4
+    out = np.full(shape, np.nan, dtype=np.float64)
+    assert calc.calculate_dose_rate(a, vs, tissue_densities=rho, out=out) is out and orc.rel_err_of_peak(out, ref_rho) <= 1e-4
+    got64 = _calc(boundary=boundary, output_dtype="float64").calculate_dose_rate(a, vs, tissue_densities=rho)
+    assert got64.dtype == np.float64 and orc.rel_err_of_peak(got64, ref_rho) <= 1e-4
+    # multi-timepoint absorbed dose through the same pipeline
+    maps = [a, (0.7 * a).astype(np.float32), (0.2 * a).astype(np.float32)]
+    t = [2.0, 24.0, 72.0]
+    w = orc.trapezoid_weights(t, 3600.0)
+    acc = sum(wi * m.astype(np.float64) for wi, m in zip(w, maps))
+    refD = (orc.conv_reference_fast if boundary == "reference" else (lambda x, kk: orc.conv_same(x, kk, fast=True)))(acc, k)
+    gotD = calc.calculate_absorbed_dose(maps, t, vs, tissue_densities=rho)
+    assert orc.rel_err_of_peak(gotD, orc.density_correct(refD, rho.astype(np.float64), 1.0, 0.1, 0.0)) <= 1e-4
+    with pytest.raises(ValueError):
+        calc.calculate_dose_rate(a, vs, tissue_densities=rho[:-1])

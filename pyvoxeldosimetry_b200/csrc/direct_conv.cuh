@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(kDirThreads) direct_conv_kernel(const __grid_c
     static_assert(ZS >= 0 && ZS + 3 + KZ - 1 <= 4 * RL - 1, "kernel too long for the staged run");
     PVD_DYN_SMEM(unsigned char, raw);
     // 128-byte aligned carve-up: [tile bx*by*bz floats][taps K0*K1*KZ floats][mbarrier]
-    float* tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~(uintptr_t)127);
+    // 128-byte aligned start, derived as an OFFSET from the dynamic shared-memory symbol so that the compiler keeps the
+    // accesses on the shared path (LDS) - rounding the pointer through an integer made them generic loads (LD)
+    float* tile = reinterpret_cast<float*>(raw + ((128u - ((unsigned)reinterpret_cast<uintptr_t>(raw) & 127u)) & 127u));
     const int box = g.bx * g.by * g.bz;
     float* taps = tile + box;
     const int ntaps = g.K0 * g.K1 * KZ;
@@ -228,6 +230,159 @@ __global__ void __launch_bounds__(kDirThreads) direct_conv_kernel(const __grid_c
                     v.w = (rho.w < g.rho_cut) ? 0.f : v.w * __fdividef(g.rho_ref, fmaxf(rho.w, g.rho_min));
                 }
                 *reinterpret_cast<float4*>(g.out + off) = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cubic kernels (K = 3, 5, 7), both boundary modes.
+//
+//  * the K^3 taps travel inside the __grid_constant__ argument struct: after full unrolling every tap is a
+//    constant-bank operand of its FFMA (c[0x0][imm]) - no tap registers, no tap loads;
+//  * each thread owns a 4 (x) x 2 (y) x 4 (z) register tile: an input row (3 x LDS.128) is loaded once and feeds
+//    4 x-outputs and 2 y-outputs - 0.6 of the shared-memory traffic of the 4 x 1 x 4 tile above, which ncu showed
+//    bound by the shared-memory pipe (l1tex 99 %);
+//  * CTA tile 8 x 16 x 64; its (8+K-1) x (16+K-1) x 72 halo box is ONE TMA load; several CTAs per SM
+//    (69 KB each for K = 5) keep the FMA pipe fed while others wait for their box;
+//  * WRAP (reference / circular boundary, kernel anchored at the origin: core/kernel_convolution.py:71-74): the halo
+//    reaches only towards lower indices; tiles whose box crosses index 0 on any axis (one tile row per axis) gather
+//    their box with modulo indexing instead of the TMA load, every other tile takes the TMA path unchanged.
+constexpr int kCubTX = 8, kCubTY = 16, kCubTZ = 64, kCubThreads = 256;
+
+template <int K>
+struct CubicArgs {
+    float taps[K * K * K];  // flipped kernel kf[i] = k[K-1-i], [x][y][z]
+    const float* in;
+    int n0, n1, n2;
+    int o0, o1, o2;         // box origin = block origin + o
+    float* out;
+    const float* density;
+    float rho_ref, rho_min, rho_cut, scale;
+    int wrap;               // circular boundary
+    int* error_flag;
+};
+
+// ZS: index of the first tap inside a staged run = (global z of tap 0 for output z) - (box origin z) - z
+template <int K, int ZS>
+__global__ void __launch_bounds__(kCubThreads) direct_conv_cubic_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                        const __grid_constant__ CubicArgs<K> g) {
+    constexpr int BX = kCubTX + K - 1, BY = kCubTY + K - 1, BZ = kCubTZ + 8;
+    constexpr int RL = 3;  // float4 loads per input run: 12 floats cover ZS + 3 + K - 1
+    static_assert(ZS >= 0 && ZS + 3 + K - 1 <= 4 * RL - 1, "kernel too long for the staged run");
+    PVD_DYN_SMEM(unsigned char, raw);
+    // 128-byte aligned start, derived as an OFFSET from the dynamic shared-memory symbol so that the compiler keeps the
+    // accesses on the shared path (LDS) - rounding the pointer through an integer made them generic loads (LD)
+    float* tile = reinterpret_cast<float*>(raw + ((128u - ((unsigned)reinterpret_cast<uintptr_t>(raw) & 127u)) & 127u));
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tile + BX * BY * BZ);
+    const int tid = threadIdx.x;
+    const int z0 = blockIdx.x * kCubTZ, y0 = blockIdx.y * kCubTY, x0 = blockIdx.z * kCubTX;
+    const int bx0 = x0 + g.o0, by0 = y0 + g.o1, bz0 = z0 + g.o2;
+#ifdef PVD_EMULATE
+    // CPU emulation of the box load: zero-filled gather
+    for (int i = tid; i < BX * BY * BZ; i += kCubThreads) {
+        const int bz = i % BZ, t = i / BZ, by = t % BY, bx = t / BY;
+        const int gx = bx0 + bx, gy = by0 + by, gz = bz0 + bz;
+        const bool inside = gx >= 0 && gx < g.n0 && gy >= 0 && gy < g.n1 && gz >= 0 && gz < g.n2;
+        tile[i] = inside ? g.in[((size_t)gx * g.n1 + gy) * g.n2 + gz] : 0.f;
+    }
+    __syncthreads();
+#else
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (unsigned)(BX * BY * BZ * sizeof(float)));
+        tma_load_3d(tile, &tmap, bar, bz0, by0, bx0);  // innermost coordinate first; out of bounds = zeros
+    }
+    mbar_wait_guarded(bar, 0, g.error_flag, 1);
+#endif
+    if (g.wrap && (bx0 < 0 || by0 < 0 || bz0 < 0)) {
+        // circular boundary: the part of the box below index 0 (zeros so far) is the wrapped data from the far end;
+        // only the one tile row per axis that touches index 0 comes here, and only its negative part is fetched
+        for (int i = tid; i < BX * BY * BZ; i += kCubThreads) {
+            const int bz = i % BZ, t = i / BZ, by = t % BY, bx = t / BY;
+            int gx = bx0 + bx, gy = by0 + by, gz = bz0 + bz;
+            if (gx < 0 || gy < 0 || gz < 0) {
+                if (gx < 0) gx += g.n0;
+                if (gy < 0) gy += g.n1;
+                if (gz < 0) gz += g.n2;
+                // beyond the high end nothing is ever used (the reach is towards lower indices only)
+                tile[i] = (gx < g.n0 && gy < g.n1 && gz < g.n2) ? g.in[((size_t)gx * g.n1 + gy) * g.n2 + gz] : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+    const int zq = tid & 15, yp = (tid >> 4) & 7, xh = tid >> 7;
+    // Accumulators as float2 pairs (z, z+1): the arithmetic is fma.rn.f32x2 (FFMA2).  A plain FFMA issues every second
+    // cycle per scheduler on this part (the 4 x 1 x 4 kernel above and a scalar version of this one both sat at
+    // 17-18 TFMA/s = the scalar FP32 pipe limit); the packed form does two FMAs per issue slot.  Bit-identical results.
+    float2 acc[4][2][2];
+    PVD_UNROLL
+    for (int x = 0; x < 4; ++x) {
+        PVD_UNROLL
+        for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = make_float2(0.f, 0.f);
+    }
+    const float* base = tile + (xh * 4) * (BY * BZ) + (2 * yp) * BZ + 4 * zq;
+    PVD_UNROLL
+    for (int ry = 0; ry < K + 1; ++ry) {      // input row ry feeds y-output 0 with ky = ry and y-output 1 with ky = ry - 1
+        PVD_UNROLL
+        for (int rx = 0; rx < 4 + K - 1; ++rx) {  // input plane rx feeds x-output x with kx = rx - x
+            float rr[RL * 4];
+            const float4* rp = reinterpret_cast<const float4*>(base + rx * (BY * BZ) + ry * BZ);
+            PVD_UNROLL
+            for (int i = 0; i < RL; ++i) {
+                const float4 v = rp[i];
+                rr[4 * i] = v.x;
+                rr[4 * i + 1] = v.y;
+                rr[4 * i + 2] = v.z;
+                rr[4 * i + 3] = v.w;
+            }
+            // the run as pairs starting at every index: (rr[i], rr[i+1]); even starts are the loaded register pairs
+            float2 pr[RL * 4 - 1];
+            PVD_UNROLL
+            for (int i = 0; i < RL * 4 - 1; ++i) pr[i] = make_float2(rr[i], rr[i + 1]);
+            PVD_UNROLL
+            for (int x = 0; x < 4; ++x) {
+                const int kx = rx - x;
+                if (kx >= 0 && kx < K) {
+                    PVD_UNROLL
+                    for (int y = 0; y < 2; ++y) {
+                        const int ky = ry - y;
+                        if (ky >= 0 && ky < K) {
+                            PVD_UNROLL
+                            for (int kz = 0; kz < K; ++kz) {
+                                const float t = g.taps[(kx * K + ky) * K + kz];  // constant bank -> uniform register
+                                const float2 tt = make_float2(t, t);
+                                acc[x][y][0] = cfma2(pr[kz + ZS], tt, acc[x][y][0]);
+                                acc[x][y][1] = cfma2(pr[kz + ZS + 2], tt, acc[x][y][1]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const int gz = z0 + 4 * zq;
+    if (gz < g.n2) {  // n2 % 4 == 0 is a precondition of this path
+        PVD_UNROLL
+        for (int y = 0; y < 2; ++y) {
+            const int gy = y0 + 2 * yp + y;
+            if (gy >= g.n1) continue;
+            PVD_UNROLL
+            for (int x = 0; x < 4; ++x) {
+                const int gx = x0 + xh * 4 + x;
+                if (gx < g.n0) {
+                    const size_t off = ((size_t)gx * g.n1 + gy) * g.n2 + gz;
+                    float4 v = make_float4(acc[x][y][0].x * g.scale, acc[x][y][0].y * g.scale, acc[x][y][1].x * g.scale, acc[x][y][1].y * g.scale);
+                    if (g.density) {
+                        const float4 rho = *reinterpret_cast<const float4*>(g.density + off);
+                        v.x = (rho.x < g.rho_cut) ? 0.f : v.x * __fdividef(g.rho_ref, fmaxf(rho.x, g.rho_min));
+                        v.y = (rho.y < g.rho_cut) ? 0.f : v.y * __fdividef(g.rho_ref, fmaxf(rho.y, g.rho_min));
+                        v.z = (rho.z < g.rho_cut) ? 0.f : v.z * __fdividef(g.rho_ref, fmaxf(rho.z, g.rho_min));
+                        v.w = (rho.w < g.rho_cut) ? 0.f : v.w * __fdividef(g.rho_ref, fmaxf(rho.w, g.rho_min));
+                    }
+                    *reinterpret_cast<float4*>(g.out + off) = v;
+                }
             }
         }
     }

@@ -237,6 +237,14 @@ __host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
     return make_float2(a.x - b.x, a.y - b.y);
 #endif
 }
+// packed fused multiply-add: (a.x * b.x + c.x, a.y * b.y + c.y), each half rounded once like fmaf
+__host__ __device__ __forceinline__ float2 cfma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__) && !defined(PVD_EMULATE) && PVD_F32X2
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
 __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

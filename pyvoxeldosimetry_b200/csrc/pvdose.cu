@@ -198,7 +198,9 @@ const FastRows kFastRows[] = {
     PVD_ROWS(432, 384, 1, 18, 24, 1),   // 400 + kernel reach
     PVD_ROWS(288, 288, 2, 16, 18, 1),
     PVD_ROWS(800, 640, 1, 8, 10, 10),          // 1024 x 1024 x 800, reference mode
-    PVD_ROWS_NOPIPE(864, 576, 8, 9, 12),       // 800 + kernel reach (tile + staging buffer exceed one SM's shared memory)
+    PVD_ROWS(840, 512, 1, 8, 7, 15),           // 800 + kernel reach ('same' mode: 825 points needed): the longest length whose
+                                               // exchange tile + 32-row staging buffer (229.9 KB) still fit one SM, so it runs pipelined
+    PVD_ROWS_NOPIPE(864, 576, 8, 9, 12),       // tile + staging buffer exceed one SM's shared memory
 };
 const FastCols* find_fast_cols(int n) {
     for (const auto& e : kFastCols)
@@ -259,6 +261,9 @@ struct pvd_plan {
     int want_algo = PVD_ALGO_AUTO;
     int dbox[3] = {0, 0, 0};
     size_t off_taps = 0, dsmem = 0;
+    bool dcubic = false;       // cubic K in {3, 5, 7}: register-tiled kernel with the taps in the argument struct
+    bool dwrap = false;        // circular (reference) boundary handled by the direct kernel
+    std::vector<float> h_taps; // flipped kernel on the host (cubic path)
     float* taps() const { return reinterpret_cast<float*>(ws + off_taps); }
     size_t off_tw[3], off_buf, off_spec, off_flag, ws_bytes;
     char* ws = nullptr;
@@ -487,19 +492,36 @@ int plan_finish(pvd_plan* p) {
         // the specialised column kernels index the work buffer with 32-bit element offsets
         if ((double)p->m[0] * p->m[1] * p->Sz >= 2147483648.0) p->fastCols[0] = p->fastCols[1] = nullptr;
     }
-    // ---- direct tiled convolution (TMA halo tiles): 'same'-type geometry, small kernels only
-    bool direct_ok = (p->k[2] == 3 || p->k[2] == 5 || p->k[2] == 7) && p->k[0] <= 9 && p->k[1] <= 9 && p->n[2] % 4 == 0;
-    for (int i = 0; i < 3; ++i) direct_ok = direct_ok && p->on[i] == p->n[i] && p->olo[i] == p->k[i] / 2;
+    // ---- direct tiled convolution (TMA halo tiles), small kernels only.  Zero-boundary 'same' geometry for any K0, K1 <= 9,
+    // K2 in {3, 5, 7}; the circular reference geometry (core/kernel_convolution.py:71-74) for cubic K in {3, 5, 7}.
+    bool same_geom = true, ref_geom = true;
+    for (int i = 0; i < 3; ++i) {
+        same_geom = same_geom && p->on[i] == p->n[i] && p->olo[i] == p->k[i] / 2;
+        ref_geom = ref_geom && p->on[i] == p->n[i] && p->olo[i] == 0 && p->m[i] == p->n[i] && p->k[i] <= p->n[i];
+    }
+    const bool kz_ok = (p->k[2] == 3 || p->k[2] == 5 || p->k[2] == 7) && p->n[2] % 4 == 0;
+    const bool cubic = kz_ok && p->k[0] == p->k[2] && p->k[1] == p->k[2];
+    const bool direct_ok = kz_ok && ((same_geom && p->k[0] <= 9 && p->k[1] <= 9) || (ref_geom && cubic));
     const long long taps = (long long)p->k[0] * p->k[1] * p->k[2];
     if (p->want_algo == PVD_ALGO_DIRECT && !direct_ok)
         return fail(PVD_ERR_UNSUPPORTED,
-                    "direct algorithm needs zero-boundary 'same' geometry, K2 in {3,5,7}, K0,K1 <= 9 and n2 %% 4 == 0");
+                    "direct algorithm needs K2 in {3,5,7}, n2 %% 4 == 0 and either zero-boundary 'same' geometry with K0,K1 <= 9 "
+                    "or the circular reference geometry with a cubic kernel no larger than the volume");
     if (direct_ok && (p->want_algo == PVD_ALGO_DIRECT || (p->want_algo == PVD_ALGO_AUTO && taps <= 125))) {
         p->algo = PVD_ALGO_DIRECT;
-        p->dbox[0] = kDirTX + p->k[0] - 1;
-        p->dbox[1] = kDirTY + p->k[1] - 1;
-        p->dbox[2] = kDirTZ + 8;  // 4 lead-in (16-byte aligned TMA start) + 64 + up to 4 right reach
-        p->dsmem = 128 + ((size_t)p->dbox[0] * p->dbox[1] * p->dbox[2] + (size_t)taps + 16) * sizeof(float) + 64;
+        p->dcubic = cubic;
+        p->dwrap = !same_geom;
+        if (cubic) {
+            p->dbox[0] = kCubTX + p->k[0] - 1;
+            p->dbox[1] = kCubTY + p->k[1] - 1;
+            p->dbox[2] = kCubTZ + 8;
+            p->dsmem = 128 + (size_t)p->dbox[0] * p->dbox[1] * p->dbox[2] * sizeof(float) + 64;
+        } else {
+            p->dbox[0] = kDirTX + p->k[0] - 1;
+            p->dbox[1] = kDirTY + p->k[1] - 1;
+            p->dbox[2] = kDirTZ + 8;  // 4 lead-in (16-byte aligned TMA start) + 64 + up to 4 right reach
+            p->dsmem = 128 + ((size_t)p->dbox[0] * p->dbox[1] * p->dbox[2] + (size_t)taps + 16) * sizeof(float) + 64;
+        }
         p->off_taps = 0;
         p->off_flag = align_up((size_t)taps * sizeof(float), 256);
         p->ws_bytes = p->off_flag + 256;
@@ -534,6 +556,53 @@ void make_col_tensor_maps(pvd_plan* p) {
 #endif
 }
 
+template <int K, int ZS>
+int launch_cubic(pvd_plan* p, const float* in, const CUtensorMap& tmap, const float* density, float rho_ref, float rho_min, float rho_cut,
+                 float scale, float* dose, cudaStream_t stream) {
+    CubicArgs<K> a;
+    memset(&a, 0, sizeof a);
+    memcpy(a.taps, p->h_taps.data(), sizeof a.taps);
+    a.in = in;
+    a.n0 = p->n[0];
+    a.n1 = p->n[1];
+    a.n2 = p->n[2];
+    const int c = p->dwrap ? 0 : K / 2;  // the circular mode anchors the kernel at the origin: centre 0
+    a.o0 = a.o1 = c - (K - 1);
+    a.o2 = p->dwrap ? -4 * ((K - 1 + 3) / 4) : -4;
+    a.out = dose;
+    a.density = density;
+    a.rho_ref = rho_ref;
+    a.rho_min = rho_min;
+    a.rho_cut = rho_cut;
+    a.scale = scale;
+    a.wrap = p->dwrap ? 1 : 0;
+    a.error_flag = p->flag();
+    const dim3 grid((unsigned)((p->n[2] + kCubTZ - 1) / kCubTZ), (unsigned)((p->n[1] + kCubTY - 1) / kCubTY),
+                    (unsigned)((p->n[0] + kCubTX - 1) / kCubTX));
+    PVD_LAUNCH((direct_conv_cubic_kernel<K, ZS>), grid, dim3(kCubThreads), p->dsmem, stream, tmap, a);
+    PVD_CUDA_CHECK("direct_conv_cubic_kernel");
+    return PVD_OK;
+}
+
+// ZS (first tap's index inside a staged 12-float run): zero boundary 4 - (K-1-K/2); circular 4*ceil((K-1)/4) - (K-1)
+int execute_direct_cubic(pvd_plan* p, const float* in, const CUtensorMap& tmap, const float* density, float rho_ref, float rho_min,
+                         float rho_cut, float scale, float* dose, cudaStream_t stream) {
+    p->npass = 0;
+    p->mark(stream, "D1 direct tiled conv (TMA halo tiles + density)", (density ? 12.0 : 8.0) * p->n[0] * p->n[1] * p->n[2]);
+    int rc;
+    if (p->dwrap) {
+        rc = p->k[2] == 3 ? launch_cubic<3, 2>(p, in, tmap, density, rho_ref, rho_min, rho_cut, scale, dose, stream)
+           : p->k[2] == 5 ? launch_cubic<5, 0>(p, in, tmap, density, rho_ref, rho_min, rho_cut, scale, dose, stream)
+                          : launch_cubic<7, 2>(p, in, tmap, density, rho_ref, rho_min, rho_cut, scale, dose, stream);
+    } else {
+        rc = p->k[2] == 3 ? launch_cubic<3, 3>(p, in, tmap, density, rho_ref, rho_min, rho_cut, scale, dose, stream)
+           : p->k[2] == 5 ? launch_cubic<5, 2>(p, in, tmap, density, rho_ref, rho_min, rho_cut, scale, dose, stream)
+                          : launch_cubic<7, 1>(p, in, tmap, density, rho_ref, rho_min, rho_cut, scale, dose, stream);
+    }
+    p->mark_end(stream);
+    return rc;
+}
+
 int execute_direct(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, const float* density, float rho_ref,
                    float rho_min, float rho_cut, float scale, float* dose, cudaStream_t stream) {
     if (T != 1) return fail(PVD_ERR_INVALID, "direct algorithm takes one activity volume: pre-accumulate with pvd_weighted_sum");
@@ -554,6 +623,7 @@ int execute_direct(pvd_plan* p, const float* const* h_act, const float* h_weight
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PVD_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
 #endif
+    if (p->dcubic) return execute_direct_cubic(p, in, tmap, density, rho_ref, rho_min, rho_cut, scale * (h_weights ? h_weights[0] : 1.f), dose, stream);
     DirectArgs a;
     memset(&a, 0, sizeof a);
     a.in = in;
@@ -580,20 +650,10 @@ int execute_direct(pvd_plan* p, const float* const* h_act, const float* h_weight
                     (unsigned)((p->n[0] + kDirTX - 1) / kDirTX));
     p->npass = 0;
     p->mark(stream, "D1 direct tiled conv (TMA halo tiles + density)", (density ? 12.0 : 8.0) * p->n[0] * p->n[1] * p->n[2]);
-    const bool cubic = p->k[0] == p->k[2];  // K0 == K2: register-resident taps, each input row loaded once
     switch (p->k[2]) {
-        case 3:
-            if (cubic) PVD_LAUNCH((direct_conv_kernel<3, 3>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
-            else PVD_LAUNCH((direct_conv_kernel<3, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
-            break;
-        case 5:
-            if (cubic) PVD_LAUNCH((direct_conv_kernel<5, 5>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
-            else PVD_LAUNCH((direct_conv_kernel<5, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
-            break;
-        default:
-            if (cubic) PVD_LAUNCH((direct_conv_kernel<7, 7>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
-            else PVD_LAUNCH((direct_conv_kernel<7, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a);
-            break;
+        case 3: PVD_LAUNCH((direct_conv_kernel<3, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
+        case 5: PVD_LAUNCH((direct_conv_kernel<5, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
+        default: PVD_LAUNCH((direct_conv_kernel<7, 0>), grid, dim3(kDirThreads), p->dsmem, stream, tmap, a); break;
     }
     PVD_CUDA_CHECK("direct_conv_kernel");
     p->mark_end(stream);
@@ -700,8 +760,10 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
     p->kernel_set = false;
     if (p->algo == PVD_ALGO_DIRECT) {
         if (PVD_SET_SMEM((direct_conv_kernel<3, 0>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_kernel<5, 0>), kMaxSmem) != 0 ||
-            PVD_SET_SMEM((direct_conv_kernel<7, 0>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_kernel<3, 3>), kMaxSmem) != 0 ||
-            PVD_SET_SMEM((direct_conv_kernel<5, 5>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_kernel<7, 7>), kMaxSmem) != 0)
+            PVD_SET_SMEM((direct_conv_kernel<7, 0>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_cubic_kernel<3, 3>), kMaxSmem) != 0 ||
+            PVD_SET_SMEM((direct_conv_cubic_kernel<3, 2>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_cubic_kernel<5, 2>), kMaxSmem) != 0 ||
+            PVD_SET_SMEM((direct_conv_cubic_kernel<5, 0>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_cubic_kernel<7, 1>), kMaxSmem) != 0 ||
+            PVD_SET_SMEM((direct_conv_cubic_kernel<7, 2>), kMaxSmem) != 0)
             return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (direct)");
         cudaMemsetAsync(p->flag(), 0, 256, stream);
         return PVD_OK;
@@ -782,6 +844,11 @@ int pvd_plan_set_kernel(pvd_plan* p, const float* kernel, void* stream_) {
     if (p->algo == PVD_ALGO_DIRECT) {
         PVD_LAUNCH(flip_kernel_kernel, dim3(4), dim3(256), 0, stream, kernel, p->taps(), p->k[0], p->k[1], p->k[2]);
         PVD_CUDA_CHECK("flip_kernel_kernel");
+        if (p->dcubic) {  // the cubic kernels take the flipped taps inside their argument struct: keep a host copy
+            p->h_taps.assign((size_t)nk, 0.f);
+            cudaMemcpyAsync(p->h_taps.data(), p->taps(), (size_t)nk * sizeof(float), cudaMemcpyDeviceToHost, stream);
+            if (cudaStreamSynchronize(stream) != cudaSuccess) return fail(PVD_ERR_CUDA, "reading the flipped taps failed");
+        }
         p->kernel_set = true;
         return PVD_OK;
     }

@@ -194,6 +194,7 @@ FAST_CASES = [
     ((2, 180, 6), (1, 7, 2), 0, 1, False),     # y <180>, persistent pipelined form
     ((3, 5, 800), (2, 2, 9), 0, 1, True),      # rows <800> 8*10*10, pipelined, one CTA per SM
     ((2, 6, 840), (1, 3, 25), 1, 1, True),     # rows <864> 8*9*12: same mode 840 -> 864, no staging pipeline
+    ((3, 5, 816), (2, 2, 49), 1, 1, True),     # rows <840> 8*7*15: same mode 816 -> 840, the longest pipelined row length
 ]
 
 
@@ -250,14 +251,43 @@ def test_direct_conv_vs_oracle(lib, shape, kshape, den):
     assert orc.rel_err_of_peak(out, ref) <= TOL
 
 
+@pytest.mark.parametrize("shape,K,den", [((16, 8, 64), 5, False), ((9, 17, 68), 3, True), ((12, 20, 72), 7, True), ((8, 8, 8), 5, True),
+                                         ((7, 7, 8), 7, False)])
+def test_direct_conv_circular_reference_mode_vs_oracle(lib, shape, K, den):
+    """Cubic K in {3, 5, 7} in the reference's circular, origin-anchored mode (core/kernel_convolution.py:71-74):
+    boundary tiles gather their halo with modulo indexing (the emulator gathers every tile)."""
+    rng = np.random.default_rng(abs(hash((shape, K))) % 2**32)
+    a = rng.uniform(0, 1e3, shape)
+    k = rng.uniform(0, 1, (K, K, K))
+    plan = lib.plan_create(shape, (K, K, K), 0, 2)  # reference boundary, PVD_ALGO_DIRECT
+    info = lib.plan_info(plan)
+    assert info.algo == 2 and info.passes == 1
+    nb = lib.plan_workspace_bytes(plan)
+    raw = np.zeros(nb + 256, np.uint8)
+    off = (-raw.ctypes.data) % 256
+    ws = raw[off:off + nb]
+    lib.plan_set_workspace(plan, ws.ctypes.data, nb)
+    k32, a32 = np.ascontiguousarray(k, np.float32), np.ascontiguousarray(a, np.float32)
+    lib.plan_set_kernel(plan, k32.ctypes.data)
+    rho = np.ascontiguousarray(rng.uniform(0.2, 2.0, shape), np.float32) if den else None
+    out = np.full(shape, np.nan, np.float32)
+    lib.conv_execute(plan, [a32.ctypes.data], None, None if rho is None else rho.ctypes.data, 1.0, 0.1, 0.0, 1.5, out.ctypes.data)
+    lib.plan_destroy(plan)
+    f = lambda x: np.asarray(x, np.float32).astype(np.float64)
+    ref = 1.5 * orc.conv_reference(f(a), f(k))
+    if den:
+        ref = orc.density_correct(ref, f(rho), 1.0, 0.1, 0.0)
+    assert orc.rel_err_of_peak(out, ref) <= TOL
+
+
 def test_algo_selection(lib):
     from pyvoxeldosimetry_b200._capi import PvdoseError
 
-    for shape, kshape, boundary, want in [((8, 8, 8), (5, 5, 5), 1, 2), ((8, 8, 8), (5, 5, 5), 0, 1), ((8, 8, 8), (7, 7, 7), 1, 1),
-                                          ((8, 8, 6), (3, 3, 3), 1, 1)]:
+    for shape, kshape, boundary, want in [((8, 8, 8), (5, 5, 5), 1, 2), ((8, 8, 8), (5, 5, 5), 0, 2), ((8, 8, 8), (7, 7, 7), 1, 1),
+                                          ((8, 8, 6), (3, 3, 3), 1, 1), ((8, 8, 8), (5, 3, 5), 0, 1), ((4, 8, 8), (5, 5, 5), 0, 1)]:
         pl = lib.plan_create(shape, kshape, boundary, 0)
         assert lib.plan_info(pl).algo == want
         lib.plan_destroy(pl)
-    with pytest.raises(PvdoseError) as e:  # circular reference semantics cannot use TMA zero fill
-        lib.plan_create((8, 8, 8), (5, 5, 5), 0, 2)
+    with pytest.raises(PvdoseError) as e:  # the circular mode exists for cubic kernels only
+        lib.plan_create((8, 8, 8), (5, 3, 5), 0, 2)
     assert e.value.code == -5

@@ -175,6 +175,31 @@ def test_direct_tma_conv_matches_oracle(torch_cuda, shape, kshape):
     assert orc.rel_err_of_peak(out, 0.75 * orc.conv_same(a.astype(np.float64), k.astype(np.float64), fast=True)) <= TOL
 
 
+@pytest.mark.parametrize("shape,K", [((64, 64, 64), 5), ((40, 36, 52), 3), ((100, 96, 92), 7), ((136, 80, 200), 5), ((8, 8, 8), 7), ((512, 32, 400), 5)])
+def test_direct_conv_circular_reference_mode(torch_cuda, shape, K):
+    """Cubic direct kernels in the reference's circular, origin-anchored mode: interior tiles by TMA, the tiles whose halo
+    crosses index 0 by a modulo gather; AUTO picks the direct path for 5^3 under the DEFAULT boundary now."""
+    from pyvoxeldosimetry_b200.engine import ConvPlan
+
+    torch = torch_cuda
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(abs(hash((shape, K))) % 2**32)
+    a = rng.uniform(0.0, 1e3, size=shape).astype(np.float32)
+    a[tuple(s // 3 for s in shape)] = 2e6
+    k = rng.uniform(0.0, 1.0, size=(K, K, K)).astype(np.float32)
+    rho = rng.choice([0.26, 1.04, 1.42], size=shape).astype(np.float32)
+    ref = orc.density_correct(orc.conv_reference_fast(a.astype(np.float64), k.astype(np.float64)), rho)
+    for algo in (2, 1, 0):
+        plan = ConvPlan(shape, (K, K, K), "reference", dev, algo)
+        want = 2 if (algo == 2 or (algo == 0 and K <= 5)) else 1
+        assert plan.info.algo == want, (algo, plan.info.algo)
+        plan.set_kernel(k)
+        out = plan.execute([torch.from_numpy(a).to(dev)], None, torch.from_numpy(rho).to(dev), scale=1.0)
+        plan.check_device_errors()
+        assert orc.rel_err_of_peak(out.cpu().numpy(), ref) <= TOL, algo
+        plan.close()
+
+
 def test_c3_full_size_vs_oracle(torch_cuda):
     """Config C3 at its full size: 512x512x400 Y90 volume, 51^3 kernel, density-corrected, reference boundary mode,
     against the float64 oracle (scipy real transforms with all host threads: same mathematics as the literal

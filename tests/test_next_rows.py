@@ -363,3 +363,52 @@ def test_gpu_dvh_vs_reference_vectors_and_numpy(gold):
         calculate_dvh(dose[:4, :4, :4], np.zeros((4, 4, 4)), 10)
     with pytest.raises(ValueError, match="same dimensions"):
         calculate_dvh(dose[:4, :4, :4], np.zeros((4, 4, 5)), 10)
+
+
+# ---- NIfTI-1 writer pinned against the standard's own struct layout (nibabel is absent in this image) ----
+# nifti_1_header of nifti1.h (NIfTI-1.1, 348 bytes), field by field, as a packed little-endian NumPy record.
+NIFTI1_STRUCT = np.dtype([
+    ("sizeof_hdr", "<i4"), ("data_type", "S10"), ("db_name", "S18"), ("extents", "<i4"), ("session_error", "<i2"), ("regular", "S1"),
+    ("dim_info", "u1"), ("dim", "<i2", (8,)), ("intent_p1", "<f4"), ("intent_p2", "<f4"), ("intent_p3", "<f4"), ("intent_code", "<i2"),
+    ("datatype", "<i2"), ("bitpix", "<i2"), ("slice_start", "<i2"), ("pixdim", "<f4", (8,)), ("vox_offset", "<f4"), ("scl_slope", "<f4"),
+    ("scl_inter", "<f4"), ("slice_end", "<i2"), ("slice_code", "u1"), ("xyzt_units", "u1"), ("cal_max", "<f4"), ("cal_min", "<f4"),
+    ("slice_duration", "<f4"), ("toffset", "<f4"), ("glmax", "<i4"), ("glmin", "<i4"), ("descrip", "S80"), ("aux_file", "S24"),
+    ("qform_code", "<i2"), ("sform_code", "<i2"), ("quatern_b", "<f4"), ("quatern_c", "<f4"), ("quatern_d", "<f4"), ("qoffset_x", "<f4"),
+    ("qoffset_y", "<f4"), ("qoffset_z", "<f4"), ("srow_x", "<f4", (4,)), ("srow_y", "<f4", (4,)), ("srow_z", "<f4", (4,)),
+    ("intent_name", "S16"), ("magic", "S4"),
+])
+
+
+def test_nifti_header_bytes_match_the_nifti1_struct(tmp_path):
+    """Byte-for-byte: the 348 header bytes the writer emits == the record the NIfTI-1 standard defines, filled with the
+    values nibabel's Nifti1Image(float32 data, affine) + header extension 44 would carry (reference core/utils.py:88-107)."""
+    _, nf = _io()
+    assert NIFTI1_STRUCT.itemsize == 348
+    rng = np.random.default_rng(44)
+    dose = rng.uniform(0, 5, (7, 5, 3)).astype(np.float32)
+    vs = (2.0, 1.5, 3.0)
+    meta = {"radionuclide": "Lu177"}
+    path = nf.save_dose_map(str(tmp_path / "pin.nii"), dose, vs, meta)
+    raw = open(path, "rb").read()
+    got = np.frombuffer(raw[:348], dtype=NIFTI1_STRUCT)[0]
+    want = np.zeros((), dtype=NIFTI1_STRUCT)
+    want["sizeof_hdr"] = 348
+    want["dim"] = (3, 7, 5, 3, 1, 1, 1, 1)
+    want["datatype"], want["bitpix"] = 16, 32                    # DT_FLOAT32
+    want["pixdim"] = (1.0, 2.0, 1.5, 3.0, 1.0, 1.0, 1.0, 1.0)     # qfac, voxel sizes
+    want["scl_slope"] = want["scl_inter"] = np.nan                # "no scaling" on disk
+    want["xyzt_units"] = 2                                        # NIFTI_UNITS_MM
+    want["descrip"] = b"Created by devhliu at 2025-02-08 09:50:56"
+    want["qform_code"], want["sform_code"] = 0, 2                 # NIFTI_XFORM_ALIGNED_ANAT
+    aff = np.diag([2.0, 1.5, 3.0, 1.0])
+    aff[:3, 3] = np.array(dose.shape) * np.array(vs) / -2.0       # reference default affine, core/utils.py:72-77
+    want["srow_x"], want["srow_y"], want["srow_z"] = aff[0], aff[1], aff[2]
+    want["magic"] = b"n+1"
+    content = open(path, "rb").read()
+    esize = int(np.frombuffer(content[352:356], "<i4")[0])
+    assert np.frombuffer(content[356:360], "<i4")[0] == 44 and esize % 16 == 0 and content[348:352] == b"\x01\x00\x00\x00"
+    want["vox_offset"] = 352 + esize
+    assert got.tobytes() == want.tobytes(), [n for n in NIFTI1_STRUCT.names if got[n].tobytes() != want[n].tobytes()]
+    # voxel data: Fortran order float32 right at vox_offset
+    data = np.frombuffer(content, "<f4", count=dose.size, offset=352 + esize).reshape(dose.shape, order="F")
+    assert np.array_equal(data, dose)

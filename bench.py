@@ -325,9 +325,11 @@ def link_peak(world: int):
     """Bare pinned cudaMemcpyAsync ceiling of the box measured by scripts/link_peak.py (profiles/r02_link_peak_<N>gpu.json):
     per-rank H2D / D2H GB/s when all `world` ranks copy at once.  None when no file exists for this N."""
     p = os.path.join(REPO, "profiles", f"r02_link_peak_{world}gpu.json")
-    if not os.path.exists(p):
+    try:  # an evidence file must never cost the bench line: tolerate banners before the JSON object, or a bad file
+        lines = [ln for ln in open(p).read().splitlines() if ln.startswith("{")]
+        d = json.loads(lines[-1])
+    except Exception:
         return None
-    d = json.load(open(p))
     return {"h2d_gbs_per_rank": d["h2d_GBs_aggregate"] / world, "d2h_gbs_per_rank": d["d2h_GBs_aggregate"] / world,
             "concurrent_gbs_per_rank_each_way": d["h2d_d2h_concurrent_GBs_aggregate_each_way"] / world, "source": os.path.basename(p)}
 

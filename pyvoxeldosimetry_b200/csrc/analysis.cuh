@@ -396,12 +396,9 @@ __global__ void __launch_bounds__(256) dvh_hist_kernel(const float* __restrict__
         if (!(x >= first && x <= last)) return;  // NaN doses are dropped, as numpy's `keep` mask does
         int idx = (int)((x - first) * inv);
         idx = idx < 0 ? 0 : (idx > bins - 1 ? bins - 1 : idx);
-        // walk to the edge-defined bin (one step in practice; two covers the rounding of the reciprocal at huge bin counts)
-        PVD_UNROLL
-        for (int it = 0; it < 2; ++it) {
-            if (x < ed[idx]) --idx;
-            else if (idx != bins - 1 && x >= ed[idx + 1]) ++idx;
-        }
+        // one step to the edge-defined bin: the guess is within +-1 (its relative error is a few 2^-24, bins <= 2^20)
+        if (x < ed[idx]) --idx;
+        else if (idx != bins - 1 && x >= ed[idx + 1]) ++idx;
         if (use_smem) atomicAdd(&s_hist[idx], 1u);
         else atomicAdd(&hist[idx], 1ull);
     };

@@ -12,6 +12,10 @@ import time
 import numpy as np
 import torch
 
+# stdout carries exactly one JSON line: NCCL prints its version banner there, so fd 1 points at stderr for the run
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 rank = int(os.environ.get("RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -136,7 +140,7 @@ if rank == 0 and world == 1:
     tmp = torch.empty(NB, dtype=torch.uint8).pin_memory()
     res["pin_memory_alloc_419MB_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
 if rank == 0:
-    print(json.dumps(res), flush=True)
+    os.write(_REAL_STDOUT, (json.dumps(res) + "\n").encode())
 if dist is not None:
     dist.barrier()
     dist.destroy_process_group()

@@ -129,8 +129,27 @@ int pvd_conv_finish(pvd_plan* plan, const float* density, float rho_min, float r
  * end-to-end caller can feed the density map plane block by plane block while earlier blocks of the dose map already
  * travel back to the host (the link is full duplex).  density / dose point at plane 0 of the full volumes. */
 int pvd_conv_middle(pvd_plan* plan, void* stream);
+/* The persistent kernels launch exactly as many CTAs as stay resident on the whole GPU, and a kernel launched with
+ * programmatic dependent launch is resident before its predecessor has finished - a concurrent kernel of ANOTHER stream
+ * (the NCCL send/recv kernel of the halo exchange) then finds no SM with room and runs only after them (measured:
+ * profiles/r02_slab_overlap_probe.jsonl).  While n_sms > 0 the persistent grids of this plan leave n_sms SMs' worth of
+ * CTA slots free; 0 restores the full grids. */
+int pvd_plan_reserve_sms(pvd_plan* plan, int n_sms);
 int pvd_conv_output_planes(pvd_plan* plan, const float* density, float rho_min, float rho_cut, float* dose, int plane_lo,
                            int plane_hi, void* stream);
+
+/* Stream-ordered 32-bit flags for the peer-memory halo exchange (no reference counterpart): once the work already
+ * enqueued on `stream` is done, write `value` to *d_flag (which may live in ANOTHER GPU's memory, mapped through CUDA IPC);
+ * hold `stream` until *d_flag >= value.  Driver stream-memory operations: no kernel, no SM - the persistent FFT kernels
+ * leave no room for one (see pvd_plan_reserve_sms).  d_flag must be 4-byte aligned memory of the CURRENT device (the
+ * driver rejects an IPC-mapped peer address, measured); a flag in a peer's memory is raised by copying a local word there
+ * with pvd_copy_async. */
+int pvd_stream_write_flag(void* d_flag, uint32_t value, void* stream);
+int pvd_stream_wait_flag_geq(void* d_flag, uint32_t value, void* stream);
+/* Stream-ordered copy between any two device addresses of the unified address space, peer (IPC-mapped) memory included:
+ * cudaMemcpyAsync, i.e. a copy engine over NVLink, no SM.  The halo planes of the slab decomposition and the 4-byte flags
+ * of their handshake travel this way (no reference counterpart). */
+int pvd_copy_async(void* dst, const void* src, size_t bytes, void* stream);
 
 int pvd_plan_destroy(pvd_plan* plan);
 

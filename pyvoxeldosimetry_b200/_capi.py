@@ -22,7 +22,7 @@ MAX_T = 16
 # every symbol include/pvdose.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "pvd_version", "pvd_build_id", "pvd_last_error", "pvd_good_fft_size", "pvd_good_fft_size_axis", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
-    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_conv_forward_planes", "pvd_conv_finish", "pvd_conv_middle", "pvd_conv_output_planes", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
+    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_conv_forward_planes", "pvd_conv_finish", "pvd_conv_middle", "pvd_conv_output_planes", "pvd_plan_reserve_sms", "pvd_stream_write_flag", "pvd_stream_wait_flag_geq", "pvd_copy_async", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
     "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
     "pvd_density_scale", "pvd_monoexp_fit", "pvd_ct_prepare", "pvd_roi_minmax", "pvd_dvh_histogram",
     "pvd_stager_create", "pvd_stager_destroy", "pvd_stage_h2d", "pvd_stage_d2h", "pvd_i16_to_f32",
@@ -88,6 +88,10 @@ class PvdLib:
         d.pvd_conv_forward_planes.argtypes = [vp, C.POINTER(vp), fp, C.c_int, C.c_float, C.c_int, C.c_int, vp]
         d.pvd_conv_finish.argtypes = [vp, vp, C.c_float, C.c_float, vp, vp]
         d.pvd_conv_middle.argtypes = [vp, vp]
+        d.pvd_plan_reserve_sms.argtypes = [vp, C.c_int]
+        d.pvd_stream_write_flag.argtypes = [vp, C.c_uint32, vp]
+        d.pvd_stream_wait_flag_geq.argtypes = [vp, C.c_uint32, vp]
+        d.pvd_copy_async.argtypes = [vp, vp, C.c_size_t, vp]
         d.pvd_conv_output_planes.argtypes = [vp, vp, C.c_float, C.c_float, vp, C.c_int, C.c_int, vp]
         d.pvd_plan_destroy.argtypes = [vp]
         d.pvd_plan_set_profiling.argtypes = [vp, C.c_int]
@@ -165,6 +169,18 @@ class PvdLib:
 
     def conv_finish(self, plan: int, density_ptr: Optional[int], rho_min: float, rho_cut: float, dose_ptr: int, stream: int = 0):
         self.check(self.dll.pvd_conv_finish(plan, density_ptr, rho_min, rho_cut, dose_ptr, stream))
+
+    def plan_reserve_sms(self, plan: int, n_sms: int):
+        self.check(self.dll.pvd_plan_reserve_sms(plan, int(n_sms)))
+
+    def stream_write_flag(self, flag_ptr: int, value: int, stream: int = 0):
+        self.check(self.dll.pvd_stream_write_flag(flag_ptr, value, stream))
+
+    def stream_wait_flag_geq(self, flag_ptr: int, value: int, stream: int = 0):
+        self.check(self.dll.pvd_stream_wait_flag_geq(flag_ptr, value, stream))
+
+    def copy_async(self, dst_ptr: int, src_ptr: int, nbytes: int, stream: int = 0):
+        self.check(self.dll.pvd_copy_async(dst_ptr, src_ptr, nbytes, stream))
 
     def conv_middle(self, plan: int, stream: int = 0):
         self.check(self.dll.pvd_conv_middle(plan, stream))

@@ -249,6 +249,14 @@ struct pvd_plan {
     const FastRows* fastRows = nullptr;
     bool usePipe = true;
     bool pdl = true;  // programmatic dependent launch of the specialised kernels
+    int sms = 0;          // SMs of the device (set with the workspace)
+    int reserve_sms = 0;  // SMs the persistent grids leave free (pvd_plan_reserve_sms): room for a concurrent NCCL kernel
+    // persistent grid of a kernel that keeps `per_sm` CTAs resident per SM: `full` CTAs fill the GPU
+    int pgrid(int full) const {
+        if (reserve_sms <= 0 || sms <= 0 || full < sms) return full;
+        const int per_sm = full / sms;
+        return std::max(per_sm, full - reserve_sms * per_sm);
+    }
     // TMA variant of the persistent y passes: tensor maps over the work buffer (forward: n[1] rows, inverse: m[1] rows)
     bool tmaRows = false;  // TMA staging in the persistent row passes
     bool tmaCols = false;
@@ -342,7 +350,7 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
     if (p->fastRows && p->usePipe && p->rowPipeGrid[0] > 0 && T == 1 && nrows < 2000000000LL && s0 % 4 == 0 && s1 % 4 == 0 &&
         ((uintptr_t)in[0] & 15) == 0) {
         const FastRows* f = p->fastRows;
-        const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[0]);
+        const int grid = (int)std::min<long long>((nrows + 31) / 32, p->pgrid(p->rowPipeGrid[0]));
         a.use_tma = 0;
         a.error_flag = p->flag() + 1;
 #ifndef PVD_EMULATE
@@ -358,7 +366,9 @@ int launch_rows_fwd(const pvd_plan* p, const float* const* in, const float* w, i
                 a.use_tma = 1;
         }
 #endif
-        PVD_LAUNCH_PDL(p->pdl, f->fwdPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
+        // with SMs reserved for a concurrent exchange kernel the first pass is a plain launch: as a programmatic dependent it
+        // would be resident (and hold every CTA slot) before the exchange kernel of the other stream becomes eligible
+        PVD_LAUNCH_PDL(p->pdl && p->reserve_sms == 0, f->fwdPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
         PVD_CUDA_CHECK("rows_fwd_pipe_kernel");
         return PVD_OK;
     }
@@ -414,7 +424,7 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
         pa.ntz_magic = (unsigned)((0x100000000ULL + pa.ntz - 1) / pa.ntz);  // exact for t * ntz < 2^32 (ntz == 1: magic wraps to 0)
         if (pa.ntz == 1) pa.ntz_magic = 0xFFFFFFFFu;
         const size_t smem = ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2);
-        const int grid = std::min(pa.ntiles, p->pipeGrid[axis][mode]);
+        const int grid = std::min(pa.ntiles, p->pgrid(p->pipeGrid[axis][mode]));
         PVD_LAUNCH_PDL(p->pdl, f->pipe[mode], dim3((unsigned)grid), dim3(f->pipeNT[mode]), smem, stream, pa);
         PVD_CUDA_CHECK("cols_pipe_kernel");
         return PVD_OK;
@@ -427,7 +437,7 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
             // normally: as a programmatic dependent this pass measured +70 us per C3 volume
             a.loop_ntz = (p->Nh + 15) / 16;
             a.loop_ntiles = a.loop_ntz * nouter;
-            const int grid = std::min(a.loop_ntiles, p->fnGrid[axis]);
+            const int grid = std::min(a.loop_ntiles, p->pgrid(p->fnGrid[axis]));
             PVD_LAUNCH_PDL(false, f->fn[mode], dim3((unsigned)grid), dim3(f->fnNT[mode]), smem, stream, a);
             PVD_CUDA_CHECK("cols_fast_kernel (looped)");
             return PVD_OK;
@@ -758,6 +768,11 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
     cudaStream_t stream = (cudaStream_t)stream_;
     p->ws = (char*)workspace;
     p->kernel_set = false;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, dev);
+    }
     if (p->algo == PVD_ALGO_DIRECT) {
         if (PVD_SET_SMEM((direct_conv_kernel<3, 0>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_kernel<5, 0>), kMaxSmem) != 0 ||
             PVD_SET_SMEM((direct_conv_kernel<7, 0>), kMaxSmem) != 0 || PVD_SET_SMEM((direct_conv_cubic_kernel<3, 3>), kMaxSmem) != 0 ||
@@ -932,6 +947,65 @@ int pvd_conv_finish(pvd_plan* p, const float* density, float rho_min, float rho_
     return conv_finish(p, density, rho_min, rho_cut, dose, (cudaStream_t)stream_, false);
 }
 
+// ---- stream-ordered 32-bit flags (cuStreamWriteValue32 / cuStreamWaitValue32): cross-GPU signalling without a kernel
+#ifndef PVD_EMULATE
+namespace {
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamValueFn get_stream_value_fn(const char* name) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<StreamValueFn>(ptr);
+    return nullptr;
+}
+}  // namespace
+int pvd_stream_write_flag(void* d_flag, uint32_t value, void* stream) {
+    static StreamValueFn fn = get_stream_value_fn("cuStreamWriteValue32");
+    if (!d_flag) return fail(PVD_ERR_INVALID, "null argument");
+    if (!fn) return fail(PVD_ERR_UNSUPPORTED, "cuStreamWriteValue32 not available from the driver");
+    const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)d_flag, value, 0 /* CU_STREAM_WRITE_VALUE_DEFAULT */);
+    if (r != CUDA_SUCCESS) return fail(PVD_ERR_CUDA, "cuStreamWriteValue32 failed with %d", (int)r);
+    return PVD_OK;
+}
+int pvd_stream_wait_flag_geq(void* d_flag, uint32_t value, void* stream) {
+    static StreamValueFn fn = get_stream_value_fn("cuStreamWaitValue32");
+    if (!d_flag) return fail(PVD_ERR_INVALID, "null argument");
+    if (!fn) return fail(PVD_ERR_UNSUPPORTED, "cuStreamWaitValue32 not available from the driver");
+    const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)d_flag, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (r != CUDA_SUCCESS) return fail(PVD_ERR_CUDA, "cuStreamWaitValue32 failed with %d", (int)r);
+    return PVD_OK;
+}
+int pvd_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!dst || !src) return fail(PVD_ERR_INVALID, "null argument");
+    if (bytes == 0) return PVD_OK;
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(PVD_ERR_CUDA, "cudaMemcpyAsync (device to device): %s", cudaGetErrorString(e));
+    return PVD_OK;
+}
+#else
+int pvd_copy_async(void* dst, const void* src, size_t bytes, void*) {
+    if (!dst || !src) return fail(PVD_ERR_INVALID, "null argument");
+    memmove(dst, src, bytes);
+    return PVD_OK;
+}
+int pvd_stream_write_flag(void* d_flag, uint32_t value, void*) {
+    if (!d_flag) return fail(PVD_ERR_INVALID, "null argument");
+    *reinterpret_cast<uint32_t*>(d_flag) = value;
+    return PVD_OK;
+}
+int pvd_stream_wait_flag_geq(void* d_flag, uint32_t value, void*) {
+    if (!d_flag) return fail(PVD_ERR_INVALID, "null argument");
+    return *reinterpret_cast<uint32_t*>(d_flag) >= value ? PVD_OK : fail(PVD_ERR_STATE, "flag not reached (emulation has no concurrency)");
+}
+#endif
+
+int pvd_plan_reserve_sms(pvd_plan* p, int n_sms) {
+    if (!p) return fail(PVD_ERR_INVALID, "null argument");
+    if (n_sms < 0 || (p->sms > 0 && n_sms >= p->sms)) return fail(PVD_ERR_INVALID, "cannot reserve %d of %d SMs", n_sms, p->sms);
+    p->reserve_sms = n_sms;
+    return PVD_OK;
+}
+
 int pvd_conv_middle(pvd_plan* p, void* stream_) {
     if (!p) return fail(PVD_ERR_INVALID, "null argument");
     if (!p->ws) return fail(PVD_ERR_STATE, "workspace not set");
@@ -1015,7 +1089,7 @@ int conv_output(pvd_plan* p, const float* density, float rho_min, float rho_cut,
     if (nrows <= 0) return PVD_OK;
     if (p->fastRows && p->usePipe && p->rowPipeGrid[1] > 0 && nrows < 2000000000LL) {
         const FastRows* f = p->fastRows;
-        const int grid = (int)std::min<long long>((nrows + 31) / 32, p->rowPipeGrid[1]);
+        const int grid = (int)std::min<long long>((nrows + 31) / 32, p->pgrid(p->rowPipeGrid[1]));
         a.use_tma = a.use_tma_den = 0;
         a.error_flag = p->flag() + 1;
 #ifndef PVD_EMULATE

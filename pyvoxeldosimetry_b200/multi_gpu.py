@@ -168,6 +168,18 @@ def _post_exchange(buf: torch.Tensor, plan: Dict, group=None) -> list:
     return dist.batch_isend_irecv(ops) if ops else []
 
 
+class _StreamWait:
+    """Request-like handle of the peer transport: wait() makes `waiter` wait for everything enqueued on `stream` so far."""
+
+    def __init__(self, stream, waiter):
+        self.event = torch.cuda.Event()
+        self.event.record(stream)
+        self.waiter = waiter
+
+    def wait(self):
+        self.waiter.wait_event(self.event)
+
+
 class SlabConvolver:
     """Rank-local half of a slab-decomposed convolution (CUDA).  Usage on every rank:
         sc = SlabConvolver(global_shape, kernel, boundary)          # after init_process_group('nccl')
@@ -176,8 +188,11 @@ class SlabConvolver:
     `rank=` / `world=` given explicitly build the geometry without a process group (single-GPU emulation of every
     rank in turn: tests, 1-GPU runs); halos are then filled with `fill_from_global`."""
 
+    # SMs the forward passes of the own planes leave free while an NCCL exchange is in flight (pvd_plan_reserve_sms)
+    EXCHANGE_SMS = 32
+
     def __init__(self, shape: Sequence[int], kernel, boundary: str = "same", group=None, device=None,
-                 rank: Optional[int] = None, world: Optional[int] = None):
+                 rank: Optional[int] = None, world: Optional[int] = None, transport: str = "auto"):
         from .engine import ConvPlan, require_cuda, to_device_f32
 
         self.group = group
@@ -207,7 +222,105 @@ class SlabConvolver:
         self.interior = self.padded[off : off + B]
         self.out = torch.empty(self.plan.out_shape, dtype=torch.float32, device=self.device)
         self.comm_stream = torch.cuda.Stream(self.device)
-        self.exchange_ms_events = None
+        # Halo transport.  "peer": every rank maps its neighbours' slab buffers (CUDA IPC) and PULLS its halo planes
+        # with peer-to-peer copies over NVLink - copy engines, no SMs, so the transfer really runs beside the forward
+        # passes; NCCL only provides the two tiny device-side barriers around it (all ranks' planes ready / all reads
+        # done).  "nccl": send/recv pairs in one group - an SM kernel that shares the SMs with the persistent FFT kernels
+        # and is starved by them (profiles/r02_slab_overlap_probe.jsonl); kept for ranks that cannot map each other.
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+        self.transport = "nccl"
+        self.peers: Dict[int, torch.Tensor] = {}
+        if self.distributed and self.world > 1 and transport in ("auto", "peer"):
+            self.transport = "peer" if self._map_peers() else "nccl"
+            if transport == "peer" and self.transport != "peer":
+                raise RuntimeError("peer transport requested but the ranks cannot map each other's buffers (CUDA IPC)")
+
+    def _map_peers(self) -> bool:
+        """Exchange CUDA IPC handles of the slab buffers and open the neighbours' ones.  Collective; every rank gets the
+        same answer (the outcome is agreed with an all-reduce)."""
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        ok = 1
+        # flags[0][p]: "rank p's own planes of epoch e are final" (written by p);  flags[1][p]: "rank p has read what it needs
+        # from me in epoch e" (written by p).  uint32 epochs, one slot per rank, in THIS rank's memory.
+        self.flags = torch.zeros((2, self.world), dtype=torch.int32, device=self.device)
+        self._epoch_word = torch.zeros(1, dtype=torch.int32, device=self.device)  # source of the remote flag copies
+        try:
+            handle = (reduce_tensor(self.padded), reduce_tensor(self.flags))
+        except Exception:
+            handle, ok = None, 0
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handle, group=self.group)
+        pull_from = sorted({p for p, _, _ in self.hplan["recvs"]})
+        push_to = sorted({p for p, _, _ in self.hplan["sends"]})
+        self.peer_flags: Dict[int, torch.Tensor] = {}
+        try:
+            for p in sorted(set(pull_from) | set(push_to)):
+                (fn, args), (ffn, fargs) = gathered[p]
+                t, f = fn(*args), ffn(*fargs)
+                if t.device == self.device or tuple(t.shape)[1:] != tuple(self.padded.shape)[1:]:
+                    raise RuntimeError("peer buffer maps onto this rank's own device")
+                self.peers[p], self.peer_flags[p] = t, f
+                # one framework copy each way: turns on direct peer access between the two devices (without it the
+                # driver stages device-to-device copies through the host)
+                keep = self.padded[:1].clone()
+                self.padded[:1].copy_(t[:1])
+                self.padded[:1].copy_(keep)
+                f[0, self.rank : self.rank + 1].copy_(self._epoch_word)
+                torch.cuda.synchronize(self.device)
+            # the stream-memory operations must exist, and a copy into every peer's flag words must be accepted
+            st0 = torch.cuda.current_stream(self.device).cuda_stream
+            self.plan.lib.stream_write_flag(self._epoch_word.data_ptr(), 0, st0)
+            self.plan.lib.stream_wait_flag_geq(self._epoch_word.data_ptr(), 0, st0)
+            for p, f in self.peer_flags.items():
+                self.plan.lib.copy_async(f[0, self.rank:].data_ptr(), self._epoch_word.data_ptr(), 4, st0)
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            self.peers.clear()
+            return False
+        self._epoch = 0
+        self._pull_from, self._push_to = pull_from, push_to
+        # where each piece sits in the peer's buffer: the k-th receive from p pairs with p's k-th send to this rank
+        plans = halo_plan(self.shape[0], self.world, self.boundary, self.kshape[0])
+        self._pulls = []
+        for p in pull_from:
+            rec = [(d, c) for (q, d, c) in self.hplan["recvs"] if q == p]
+            snd = [(s, c) for (q, s, c) in plans[p]["sends"] if q == self.rank]
+            for (d, c), (s0, c2) in zip(rec, snd):
+                assert c == c2
+                self._pulls.append((p, s0, d, c))
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        return True
+
+    def _peer_exchange(self) -> None:
+        """On the current (comm) stream, without a single kernel: tell the ranks that pull from me that my planes are
+        final, wait for the owners of my halo planes to say the same, pull the planes with peer-to-peer copies (copy
+        engines over NVLink), tell the owners I am done, and wait until everybody who reads my planes is done too.
+        Waits are stream-memory operations on THIS rank's flag words; a flag in a peer's memory is raised by copying the
+        epoch word there (the driver refuses cuStreamWriteValue32 on an IPC-mapped address)."""
+        lib = self.plan.lib
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self._epoch += 1
+        e, r = self._epoch, self.rank
+        plane_bytes = self.padded[0].numel() * 4
+        lib.stream_write_flag(self._epoch_word.data_ptr(), e, st)
+        src = self._epoch_word.data_ptr()
+        for p in self._push_to:   # my planes are final (this stream has waited for the compute stream)
+            lib.copy_async(self.peer_flags[p][0, r:].data_ptr(), src, 4, st)
+        for p in self._pull_from:
+            lib.stream_wait_flag_geq(self.flags[0, p:].data_ptr(), e, st)
+        for p, s0, d0, cnt in self._pulls:
+            lib.copy_async(self.padded[d0:].data_ptr(), self.peers[p][s0:].data_ptr(), cnt * plane_bytes, st)
+        for p in self._pull_from:  # done reading p's planes
+            lib.copy_async(self.peer_flags[p][1, r:].data_ptr(), src, 4, st)
+        for p in self._push_to:    # my planes may be rewritten once every reader is done
+            lib.stream_wait_flag_geq(self.flags[1, p:].data_ptr(), e, st)
 
     # -------------------------------------------------------------- emulation helper (no process group)
     def fill_from_global(self, volume: torch.Tensor) -> None:
@@ -241,7 +354,11 @@ class SlabConvolver:
                 # the exchange runs on its own stream: it needs the interior planes (sends) but nothing else
                 self.comm_stream.wait_stream(main)
                 with torch.cuda.stream(self.comm_stream):
-                    reqs = _post_exchange(self.padded, self.hplan, self.group)
+                    if self.transport == "peer":
+                        self._peer_exchange()
+                        reqs = [_StreamWait(self.comm_stream, main)]
+                    else:
+                        reqs = _post_exchange(self.padded, self.hplan, self.group)
                 if not overlap:
                     for r in reqs:
                         r.wait()
@@ -251,7 +368,9 @@ class SlabConvolver:
                     self.padded[dst : dst + cnt].copy_(self.padded[src : src + cnt])
             if reqs:
                 # own planes first, while the halo planes are in flight ...
+                lib.plan_reserve_sms(h, self.EXCHANGE_SMS if self.transport == "nccl" else 0)
                 lib.conv_forward_planes(h, ptr, None, gain, off, off + B, main.cuda_stream)
+                lib.plan_reserve_sms(h, 0)
                 for r in reqs:
                     r.wait()  # stream-level: `main` waits for the NCCL work, the host does not
                 # ... then the halo planes below and above

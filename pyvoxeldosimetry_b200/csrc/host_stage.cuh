@@ -12,7 +12,10 @@
 //   D2H  the calling thread enqueues chunk copies into free ring slots; workers wait for a slot's event and copy
 //        (float32) or widen (float64) it into the caller's array; the call returns when the array is complete.
 // Eight threads moved 71 GB/s pageable -> pinned on the box (16: 48 GB/s, profiles/r02_link_peak_1gpu.json), above the
-// 55 GB/s of the PCIe link, so the link stays the limit.
+// 55 GB/s of the PCIe link, so the link stays the limit.  While a download runs beside an upload the HOST memory system is
+// what saturates (measured: staged upload + pinned download of one volume each 14.2 ms against 8.6 ms pinned both ways,
+// profiles/r02_e2e_breakdown.jsonl), so the staging copies use non-temporal stores: no read-for-ownership of the
+// destination lines, a third less host-memory traffic per staged byte.
 #pragma once
 #include "pvd_common.cuh"
 
@@ -23,6 +26,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include "host_copy.h"
 
 namespace pvd {
 
@@ -75,11 +79,9 @@ public:
                     if (e != cudaSuccess) err_.store(e);
                 }
                 if (dtype == HD_F64) {
-                    const double* s = static_cast<const double*>(src) + e0;
-                    float* d = reinterpret_cast<float*>(stage);
-                    for (size_t i = 0; i < cnt; ++i) d[i] = (float)s[i];
+                    stream_narrow(reinterpret_cast<float*>(stage), static_cast<const double*>(src) + e0, cnt);
                 } else {
-                    memcpy(stage, static_cast<const char*>(src) + e0 * heb, cnt * heb);
+                    stream_copy(stage, static_cast<const char*>(src) + e0 * heb, cnt * heb);
                 }
                 {
                     // one enqueue at a time keeps (copy, event) pairs adjacent in the stream
@@ -141,10 +143,9 @@ public:
                 const float* s = reinterpret_cast<const float*>(pinned_ + (size_t)slot * chunk_);
                 const size_t e0 = c * per, cnt = (e0 + per <= n) ? per : n - e0;
                 if (dtype == HD_F64) {
-                    double* d = static_cast<double*>(dst) + e0;
-                    for (size_t i = 0; i < cnt; ++i) d[i] = (double)s[i];
+                    stream_widen(static_cast<double*>(dst) + e0, s, cnt);
                 } else {
-                    memcpy(static_cast<float*>(dst) + e0, s, cnt * 4);
+                    stream_copy(static_cast<float*>(dst) + e0, s, cnt * 4);
                 }
                 finish_slot_turn(slot);
             }

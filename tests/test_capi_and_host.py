@@ -155,3 +155,40 @@ def test_shard_range_and_slab_geometry():
     assert g["ex"]["out_lo"][0] == 50 and g["ex"]["out_n"] == (128, 1024, 800) and g["ex"]["m"][0] >= 178
     g = slab_geometry((1024, 1024, 800), (51, 51, 51), "reference", 8, 0, emu_lib())
     assert (g["need_lo"], g["need_hi"]) == (-50, 128) and g["ex"]["out_lo"] == (50, 0, 0) and g["ex"]["m"][1:] == (1024, 800)
+
+
+def test_streaming_host_copies(tmp_path):
+    """The staging threads' non-temporal copies / conversions (csrc/host_copy.h, plain C++): every head / tail alignment,
+    float64 -> float32 rounds like NumPy's astype, float32 -> float64 is exact."""
+    import ctypes
+
+    src = tmp_path / "hc.cpp"
+    src.write_text('#include "host_copy.h"\n'
+                   'extern "C" void hc_copy(void* d, const void* s, size_t n) { pvd::stream_copy(d, s, n); }\n'
+                   'extern "C" void hc_narrow(float* d, const double* s, size_t n) { pvd::stream_narrow(d, s, n); }\n'
+                   'extern "C" void hc_widen(double* d, const float* s, size_t n) { pvd::stream_widen(d, s, n); }\n')
+    so = tmp_path / "hc.so"
+    csrc = os.path.join(REPO, "pyvoxeldosimetry_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", f"-I{csrc}", "-o", str(so), str(src)], check=True)
+    dll = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(3)
+    raw = rng.integers(0, 256, 5000, dtype=np.uint8)
+    for off_s in (0, 1, 7):
+        for off_d in (0, 3, 4, 15):
+            for n in (0, 1, 15, 16, 63, 64, 65, 200, 4096 + 13):
+                dst = np.zeros(n + 64, dtype=np.uint8)
+                dll.hc_copy(ctypes.c_void_p(dst.ctypes.data + off_d), ctypes.c_void_p(raw.ctypes.data + off_s), ctypes.c_size_t(n))
+                assert np.array_equal(dst[off_d : off_d + n], raw[off_s : off_s + n])
+                assert not dst[:off_d].any() and not dst[off_d + n :].any()
+    d64 = np.concatenate([rng.standard_normal(1003) * 10.0 ** rng.integers(-30, 30, 1003), [0.0, -0.0, 1e300, -1e300, 1e-320, np.inf]])
+    with np.errstate(over="ignore"):
+        want32 = d64.astype(np.float32)
+    for off in (0, 1, 2, 3):
+        for n in (0, 1, 3, 4, 5, 8, 1009):
+            buf = np.zeros(n + 8, dtype=np.float32)
+            dll.hc_narrow(ctypes.c_void_p(buf.ctypes.data + 4 * off), ctypes.c_void_p(d64.ctypes.data), ctypes.c_size_t(n))
+            assert np.array_equal(buf[off : off + n], want32[:n]) and not buf[:off].any() and not buf[off + n :].any()
+            wide = np.zeros(n + 4, dtype=np.float64)
+            dll.hc_widen(ctypes.c_void_p(wide.ctypes.data + 8 * (off & 1)), ctypes.c_void_p(want32.ctypes.data), ctypes.c_size_t(n))
+            o = off & 1
+            assert np.array_equal(wide[o : o + n], want32[:n].astype(np.float64)) and not wide[o + n :].any()

@@ -54,7 +54,7 @@ WORKLOADS = {
     "c4": dict(shape=(256, 256, 256), kgrid=(31, 31, 31), nuclide="Lu177", voxel=4.8, T=4, density=False, volumes=64,
                desc="C4: 64 patient volumes (256^3, 4 time points, 31^3 DVK) sharded over the ranks"),
     "c5": dict(shape=(1024, 1024, 800), kgrid=(51, 51, 51), nuclide="Y90", voxel=1.0, T=1, density=True,
-               desc="C5: 1024x1024x800 volume, 51^3 DVK, slabs along axis 0 + kernel-radius halo exchange (NCCL send/recv)"),
+               desc="C5: 1024x1024x800 volume, 51^3 DVK, slabs along axis 0 + kernel-radius halo exchange over NVLink"),
 }
 
 
@@ -494,8 +494,9 @@ def run_c4(args, dev, dist, rank, world, steps):
 
 def run_c5(args, dev, dist, rank, world, steps, boundary):
     """C5: one 1024x1024x800 volume, 51^3 Y90 kernel, density-corrected.  N = 1: the whole volume on one GPU (the strong-
-    scaling anchor).  N > 1: slabs along axis 0, kernel-radius halo exchange with NCCL send/recv on a side stream, hidden
-    behind the plane-local passes of the rank's own planes; the stitched slab result is compared with a single-GPU
+    scaling anchor).  N > 1: slabs along axis 0, kernel-radius halo exchange over NVLink on a side stream (peer-memory
+    pulls by the copy engines, NCCL send/recv where the ranks cannot map each other), hidden behind the plane-local passes of
+    the rank's own planes; the stitched slab result is compared with a single-GPU
     convolution of the whole volume on rank 0 (parity of the NCCL data path, inside the driver-run bench)."""
     import torch
 
@@ -536,7 +537,10 @@ def run_c5(args, dev, dist, rank, world, steps, boundary):
         ms_compute = time_steps(lambda: sc(density_slab=rho, exchange=False), max(3, steps // 2), 2, dev, dist)
         sc.check_device_errors()
         halo = sc.geom["n"][0] - (sc.hi - sc.lo)
-        res.update({"decomposition": f"{world} slabs along axis 0 + NCCL halo exchange (send/recv in one group, side stream, overlapped)",
+        how = ("halo planes pulled from the neighbours' mapped buffers by copy-engine peer copies (CUDA IPC, stream-ordered flag handshake, no SM)"
+               if sc.transport == "peer" else "NCCL send/recv in one group, 32 SMs reserved for it")
+        res.update({"decomposition": f"{world} slabs along axis 0 + halo exchange on a side stream under the forward passes of the own planes: {how}",
+                    "halo_transport": sc.transport,
                     "slab_planes": sc.hi - sc.lo, "halo_planes": halo, "halo_bytes_received_per_rank": int(halo * shape[1] * shape[2] * 4),
                     "local_fft_shape": list(sc.plan.fft_shape), "ms_exchange_not_overlapped": round(ms_serial, 4),
                     "ms_without_exchange": round(ms_compute, 4), "exchange_exposed_ms": round(ms - ms_compute, 4), "gpu_launches_per_volume": 7})

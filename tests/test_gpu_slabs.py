@@ -1,8 +1,12 @@
 """GPU tests of the z-slab decomposition that need ONE GPU: every rank's local plan is run in
 turn on the same device (`SlabConvolver(rank=, world=)`, halos filled from the global volume exactly as the NCCL exchange
-delivers them), the slabs are stitched and compared with the whole-volume plan and with the float64 oracle.  The NCCL
-exchange itself is covered by tests/test_distributed_cpu.py (gloo, schedule logic) and, on multi-GPU boxes, by
-bench.py's C5 leg, which checks the stitched slab result against a single-GPU run on every N > 1 launch."""
+delivers them), the slabs are stitched and compared with the whole-volume plan and with the float64 oracle.  The
+exchange itself is covered by tests/test_distributed_cpu.py (gloo, schedule logic), by the two-process test at the end of
+this file where two GPUs are visible, and by bench.py's C5 leg, which checks the stitched slab result against a single-GPU
+run on every N > 1 launch."""
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -142,3 +146,28 @@ def test_c5_full_size_eight_slabs_vs_whole_volume_and_properties():
         a[p] += 3e9
         ref = orc.conv_same(a.cpu().numpy().astype(np.float64), k.astype(np.float64), fast=True)
         assert orc.rel_err_of_peak(full.cpu().numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_two_process_halo_exchange_matches_the_whole_volume(transport):
+    """The real exchange (one process per GPU, torchrun): mapped-peer-memory pulls and the NCCL send/recv fallback, both
+    boundary modes, several epochs on one SlabConvolver.  Needs two GPUs (the driver's scaling boxes; skipped on one)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SLAB_TRANSPORT=transport)
+    port = 29531 + (transport == "nccl")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(repo, "scripts", "multi_gpu_check.py")], cwd=repo, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["transport"] == transport
+    errs = [v for k, v in res.items() if k.startswith("slab_")]
+    assert len(errs) == 3 and max(errs) < 1e-5

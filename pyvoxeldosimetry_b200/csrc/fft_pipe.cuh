@@ -42,8 +42,8 @@ template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 #endif
 
 struct ColPipeArgs {
-    // TMA variant (use_tma): the tile [N indices][16 frequencies] is a 3-D box of this tensor map over the work buffer
-    // - dims (2*Sz floats, rows, outer), box (32 floats, BOXR rows, 1) - so ONE thread issues N/BOXR bulk copies per
+    // TMA variant (use_tma): the tile [N indices][W frequencies] is a 3-D box of this tensor map over the work buffer
+    // - dims (2*Sz floats, rows, outer), box (2*W floats, BOXR rows, 1) - so ONE thread issues N/BOXR bulk copies per
     // tile instead of N*8/NT 16-byte cp.async per thread (ncu: mio_throttle was the top stall of the y passes).
     alignas(64) CUtensorMap tmap;
     ColArgs c;
@@ -62,16 +62,19 @@ constexpr int tma_box_rows(int n) {
     return best;
 }
 
-template <int N, int NT, int MINB, int R1, int R2, int R3, int MODE>
+// W = frequencies per tile: 16 (full 128-byte lines) wherever two N x 16 buffers fit one SM; 8 (64-byte half lines) for
+// the 1024- and 1152-point y passes, whose full-line tile (131 / 147 KB) could only run unpipelined, one tile per CTA.
+template <int N, int NT, int MINB, int R1, int R2, int R3, int MODE, int W = 16>
 __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const __grid_constant__ ColPipeArgs pa) {
-    constexpr int W = 16;
-    using LS_ = LastStage<N, NT, R1, R2, R3>;
+    static_assert(W == 16 || W == 8, "tile width: full or half 128-byte lines");
+    constexpr int CPR = W / 2;  // 16-byte chunks per tile row
+    using LS_ = LastStage<N, NT, R1, R2, R3, W>;
     constexpr int RL = LS_::RL, TPC = LS_::TPC, BPTL = LS_::BPT;
     using Fwd = Sched<N, R1, R2, R3>;
     using Rev = Sched<N, (R3 > 1 ? R3 : R2), (R3 > 1 ? R2 : R1), (R3 > 1 ? R1 : 1)>;
     constexpr bool SYM = (R3 > 1) ? (R1 == R3) : (R1 == R2);
-    constexpr int CHUNKS = N * 8;  // 16-byte chunks per tile
-    static_assert(CHUNKS % NT == 0 && NT % 8 == 0, "tile must split evenly over the threads");
+    constexpr int CHUNKS = N * CPR;  // 16-byte chunks per tile
+    static_assert(CHUNKS % NT == 0 && NT % CPR == 0, "tile must split evenly over the threads");
     const ColArgs& g = pa.c;
     PVD_DYN_SMEM(float2, smem);
     float2* tws = smem + 2 * N * W;
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const __grid_consta
     const int n_in = g.n_in;
     const unsigned cnt = (unsigned)g.out_n;
     const int ntz = pa.ntz, ntiles = pa.ntiles;
-    const int crow = threadIdx.x >> 3, ccol = (threadIdx.x & 7) * 2;  // this thread's chunk inside a row group
+    const int crow = threadIdx.x / CPR, ccol = (threadIdx.x % CPR) * 2;  // this thread's chunk inside a row group
     const int wl = threadIdx.x % W, b0 = threadIdx.x / W;
     const int blo = b0 - g.out_lo;
     const size_t toff = (size_t)b0 * es + wl;  // this thread's element inside a tile (stage-1 input / last-stage output)
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_pipe_kernel(const __grid_consta
         float2* dstp = buf + crow * W + ccol;
         PVD_UNROLL
         for (int i = 0; i < CHUNKS / NT; ++i)
-            cp_async16(dstp + i * ((NT / 8) * W), eptr(src, esb, i * (NT / 8)), crow + i * (NT / 8) < n_in);
+            cp_async16(dstp + i * ((NT / CPR) * W), eptr(src, esb, i * (NT / CPR)), crow + i * (NT / CPR) < n_in);
     };
 #ifndef PVD_EMULATE
     constexpr int BOXR = tma_box_rows(N);

@@ -124,6 +124,7 @@ struct FastCols {
     ColPipeKernelFn pipe[4];  // persistent cp.async-pipelined variant (null: use fn for that mode)
     int pipeNT[4];            // threads per CTA of each pipelined variant
     int fnNT[4];              // threads per CTA of each one-tile-per-CTA variant
+    int pipeW;                // frequencies per tile of the pipelined variants (16 = full 128-byte lines, 8 = half lines)
 };
 struct FastRows {
     int N, NT;
@@ -144,7 +145,7 @@ struct FastRows {
             cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_CONV>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC> \
     }
 #define PVD_COLS(N, NT, MINB, R1, R2, R3) \
-    { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), PVD_COLS_PIPE(N, NT, MINB, R1, R2, R3), {NT, NT, NT, NT}, {NT, NT, NT, NT} }
+    { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), PVD_COLS_PIPE(N, NT, MINB, R1, R2, R3), {NT, NT, NT, NT}, {NT, NT, NT, NT}, 16 }
 // As PVD_COLS, but the forward*spectrum*inverse pass (issue-bound, 2 transforms per tile) runs the one-tile-per-CTA
 // kernel with its own schedule (X1, X2, X3), NTX threads and MINBX CTAs per SM: fewer radix stages = fewer
 // block-wide barriers, and independent CTAs overlap each other's memory and arithmetic phases
@@ -156,7 +157,7 @@ struct FastRows {
              cols_fast_kernel<N, NTX, X1, X2, X3, COL_CONV, MINBX>, cols_fast_kernel<N, NT, R1, R2, R3, COL_SPEC>}, \
             {cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_FWD>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_INV>, \
              nullptr, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC>},                                         \
-            {NT, NT, 0, NT}, {NT, NT, NTX, NT}                                                                     \
+            {NT, NT, 0, NT}, {NT, NT, NTX, NT}, 16                                                                 \
     }
 // NTC threads for the (issue-bound) forward*spectrum*inverse variant, NT for the others
 #define PVD_COLS_C(N, NT, MINB, NTC, R1, R2, R3)                                                                \
@@ -164,10 +165,22 @@ struct FastRows {
         N, NT, PVD_COLS_FN(N, NT, R1, R2, R3),                                                                  \
             {cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_FWD>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_INV>, \
              cols_pipe_kernel<N, NTC, 1, R1, R2, R3, COL_CONV>, cols_pipe_kernel<N, NT, MINB, R1, R2, R3, COL_SPEC>}, \
-            {NT, NT, NTC, NT}, {NT, NT, NT, NT}                                                                 \
+            {NT, NT, NTC, NT}, {NT, NT, NT, NT}, 16                                                             \
     }
 #define PVD_COLS_NOPIPE(N, NT, R1, R2, R3) \
-    { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), {nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}, {NT, NT, NT, NT} }
+    { N, NT, PVD_COLS_FN(N, NT, R1, R2, R3), {nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}, {NT, NT, NT, NT}, 16 }
+// Long transforms (1024, 1152): two full-line tiles do not fit one SM, so the forward / inverse / spectrum passes run the
+// persistent double-buffered kernel on HALF-line tiles (N x 8 frequencies, NTP threads, TMA-staged), while the
+// forward*spectrum*inverse pass keeps the full-line kernel (64-byte accesses at a plane stride waste DRAM pages: measured
+// 0.457 vs 0.262 ms at 512) as a tile walk; prefetching the next tile's lines into L2 from inside the walk made it SLOWER
+// (1024: 3.35 -> 4.18 ms, 1152: 3.70 -> 5.34 ms, profiles/r02_ab_long_columns.jsonl) and is not in the code.
+#define PVD_COLS_HALF(N, NT, NTP, R1, R2, R3)                                                                          \
+    {                                                                                                                  \
+        N, NT, PVD_COLS_FN(N, NT, R1, R2, R3),                                                                         \
+            {cols_pipe_kernel<N, NTP, 1, R1, R2, R3, COL_FWD, 8>, cols_pipe_kernel<N, NTP, 1, R1, R2, R3, COL_INV, 8>, \
+             nullptr, cols_pipe_kernel<N, NTP, 1, R1, R2, R3, COL_SPEC, 8>},                                           \
+            {NTP, NTP, 0, NTP}, {NT, NT, NT, NT}, 8                                                                    \
+    }
 #define PVD_ROWS(N, NT, MINB, R1, R2, R3)                                                                  \
     {                                                                                                      \
         N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>,           \
@@ -183,10 +196,10 @@ const FastCols kFastCols[] = {
     PVD_COLS(576, 384, 1, 24, 24, 1),   // 512 + kernel reach ('same' mode of 512-wide volumes)
     PVD_COLS(432, 384, 1, 18, 24, 1),
     PVD_COLS(288, 288, 2, 16, 18, 1),   // 256 + kernel reach
-    PVD_COLS_NOPIPE(1024, 1024, 16, 8, 8),
+    PVD_COLS_HALF(1024, 1024, 512, 16, 8, 8),
     // slab decomposition of the 1024 x 1024 x 800 volume ('same' mode): 1024 + reach -> 1152, slabs of
     // 256 / 128 planes + 50 halo planes -> 320 / 180 (192: other kernel sizes)
-    PVD_COLS_NOPIPE(1152, 768, 8, 12, 12),
+    PVD_COLS_HALF(1152, 768, 384, 8, 12, 12),
     PVD_COLS(320, 320, 2, 16, 20, 1),
     PVD_COLS(192, 256, 3, 12, 16, 1),
     PVD_COLS(180, 288, 3, 10, 18, 1),   // 128-plane slab + 50 halo planes = 178 -> 180 (8 ranks; 192 costs 6.7 % more points)
@@ -419,11 +432,11 @@ int launch_cols(const pvd_plan* p, int axis, int mode, const float2* in, float2*
             pa.use_tma = 1;
         }
         pa.c = a;
-        pa.ntz = (p->Nh + 15) / 16;
+        pa.ntz = (p->Nh + f->pipeW - 1) / f->pipeW;
         pa.ntiles = pa.ntz * nouter;
         pa.ntz_magic = (unsigned)((0x100000000ULL + pa.ntz - 1) / pa.ntz);  // exact for t * ntz < 2^32 (ntz == 1: magic wraps to 0)
         if (pa.ntz == 1) pa.ntz_magic = 0xFFFFFFFFu;
-        const size_t smem = ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2);
+        const size_t smem = ((size_t)f->N * 2 * f->pipeW + 4 * f->N) * sizeof(float2);
         const int grid = std::min(pa.ntiles, p->pgrid(p->pipeGrid[axis][mode]));
         PVD_LAUNCH_PDL(p->pdl, f->pipe[mode], dim3((unsigned)grid), dim3(f->pipeNT[mode]), smem, stream, pa);
         PVD_CUDA_CHECK("cols_pipe_kernel");
@@ -555,7 +568,7 @@ void make_col_tensor_maps(pvd_plan* p) {
         memset(&p->tmapCols[i], 0, sizeof(CUtensorMap));
         const cuuint64_t gdim[3] = {(cuuint64_t)2 * p->Sz, (cuuint64_t)rows[i], (cuuint64_t)p->m[0]};
         const cuuint64_t gstr[2] = {(cuuint64_t)p->Sz * 8, (cuuint64_t)p->m[1] * p->Sz * 8};
-        const cuuint32_t box[3] = {32, (cuuint32_t)tma_box_rows(f->N), 1};
+        const cuuint32_t box[3] = {(cuuint32_t)(2 * f->pipeW), (cuuint32_t)tma_box_rows(f->N), 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         if (enc(&p->tmapCols[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->buf(), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -812,7 +825,8 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
                     int dev = 0, sms = 0, per = 0;
                     cudaGetDevice(&dev);
                     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->pipe[md], f->pipeNT[md], ((size_t)f->N * 32 + 4 * f->N) * sizeof(float2));
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->pipe[md], f->pipeNT[md],
+                                                                  ((size_t)f->N * 2 * f->pipeW + 4 * f->N) * sizeof(float2));
                     p->pipeGrid[a][md] = sms * per;  // one resident wave: every CTA stays on its SM and loops
                 }
             }

@@ -475,9 +475,10 @@ def run_c4(args, dev, dist, rank, world, steps):
     w = trapezoid_weights([4.0, 24.0, 96.0, 168.0], 3600.0)
     out = torch.empty(plan.out_shape, device=dev)
 
-    def step():
-        for v in mine:
-            plan.execute(sets[v & 1], w, None, out=out)
+    batch_acts, batch_outs = [sets[v & 1] for v in mine], [out] * len(mine)
+
+    def step():  # the rank's whole share in ONE batched C-ABI call (pvd_conv_execute_batch)
+        plan.execute_batch(batch_acts, w, None, outs=batch_outs)
 
     ms = time_steps(step, steps, 3, dev, dist)
     plan.check_device_errors()

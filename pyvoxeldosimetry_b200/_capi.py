@@ -22,7 +22,7 @@ MAX_T = 16
 # every symbol include/pvdose.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "pvd_version", "pvd_build_id", "pvd_last_error", "pvd_good_fft_size", "pvd_good_fft_size_axis", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
-    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_conv_forward_planes", "pvd_conv_finish", "pvd_conv_middle", "pvd_conv_output_planes", "pvd_plan_reserve_sms", "pvd_stream_write_flag", "pvd_stream_wait_flag_geq", "pvd_copy_async", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
+    "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_conv_execute_batch", "pvd_conv_forward_planes", "pvd_conv_finish", "pvd_conv_middle", "pvd_conv_output_planes", "pvd_plan_reserve_sms", "pvd_stream_write_flag", "pvd_stream_wait_flag_geq", "pvd_copy_async", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
     "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
     "pvd_density_scale", "pvd_monoexp_fit", "pvd_ct_prepare", "pvd_roi_minmax", "pvd_dvh_histogram",
     "pvd_stager_create", "pvd_stager_destroy", "pvd_stage_h2d", "pvd_stage_d2h", "pvd_i16_to_f32",
@@ -85,6 +85,8 @@ class PvdLib:
         d.pvd_plan_set_workspace.argtypes = [vp, vp, C.c_size_t, vp]
         d.pvd_plan_set_kernel.argtypes = [vp, vp, vp]
         d.pvd_conv_execute.argtypes = [vp, C.POINTER(vp), fp, C.c_int, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
+        d.pvd_conv_execute_batch.argtypes = [vp, C.POINTER(vp), fp, C.c_int, C.POINTER(vp), C.c_float, C.c_float, C.c_float, C.c_float,
+                                             C.POINTER(vp), C.c_int, vp]
         d.pvd_conv_forward_planes.argtypes = [vp, C.POINTER(vp), fp, C.c_int, C.c_float, C.c_int, C.c_int, vp]
         d.pvd_conv_finish.argtypes = [vp, vp, C.c_float, C.c_float, vp, vp]
         d.pvd_conv_middle.argtypes = [vp, vp]
@@ -159,6 +161,20 @@ class PvdLib:
         ptrs = (C.c_void_p * T)(*act_ptrs)
         w = (C.c_float * T)(*[float(x) for x in weights]) if weights is not None else None
         self.check(self.dll.pvd_conv_execute(plan, ptrs, w, T, density_ptr, rho_ref, rho_min, rho_cut, scale, dose_ptr, stream))
+
+    def conv_execute_batch(self, plan: int, act_ptrs: Sequence[Sequence[int]], weights: Optional[Sequence[float]],
+                           density_ptrs: Optional[Sequence[Optional[int]]], rho_ref: float, rho_min: float, rho_cut: float, scale: float,
+                           dose_ptrs: Sequence[int], stream: int = 0):
+        """act_ptrs[b][t]; density_ptrs None or one entry (pointer or None) per volume; dose_ptrs one per volume."""
+        B = len(act_ptrs)
+        T = len(act_ptrs[0]) if B else 1
+        if any(len(a) != T for a in act_ptrs) or len(dose_ptrs) != B or (density_ptrs is not None and len(density_ptrs) != B):
+            raise ValueError("every volume of a batch needs T activity pointers, one output and (optionally) one density pointer")
+        flat = (C.c_void_p * max(1, B * T))(*[p for a in act_ptrs for p in a])
+        w = (C.c_float * T)(*[float(x) for x in weights]) if weights is not None else None
+        den = (C.c_void_p * max(1, B))(*density_ptrs) if density_ptrs is not None else None
+        outs = (C.c_void_p * max(1, B))(*dose_ptrs)
+        self.check(self.dll.pvd_conv_execute_batch(plan, flat, w, T, den, rho_ref, rho_min, rho_cut, scale, outs, B, stream))
 
     def conv_forward_planes(self, plan: int, act_ptrs: Sequence[int], weights: Optional[Sequence[float]], gain: float, lo: int, hi: int,
                             stream: int = 0):

@@ -942,6 +942,19 @@ int pvd_conv_execute(pvd_plan* p, const float* const* h_act, const float* h_weig
     return conv_finish(p, density, rho_min, rho_cut, dose, stream, true);
 }
 
+int pvd_conv_execute_batch(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, const float* const* h_density,
+                           float rho_ref, float rho_min, float rho_cut, float scale, float* const* h_dose, int batch, void* stream_) {
+    if (!p || !h_act || !h_dose) return fail(PVD_ERR_INVALID, "null argument");
+    if (batch < 0) return fail(PVD_ERR_INVALID, "batch must not be negative");
+    for (int b = 0; b < batch; ++b) {
+        if (!h_dose[b]) return fail(PVD_ERR_INVALID, "null output pointer for volume %d", b);
+        if (int rc = pvd_conv_execute(p, h_act + (size_t)b * T, h_weights, T, h_density ? h_density[b] : nullptr, rho_ref, rho_min, rho_cut,
+                                      scale, h_dose[b], stream_))
+            return rc;
+    }
+    return PVD_OK;
+}
+
 int pvd_conv_forward_planes(pvd_plan* p, const float* const* h_act, const float* h_weights, int T, float gain, int plane_lo,
                             int plane_hi, void* stream_) {
     if (!p || !h_act) return fail(PVD_ERR_INVALID, "null argument");

@@ -212,6 +212,39 @@ class ConvPlan:
                                   rho_ref, rho_min, rho_cut, scale, out.data_ptr(), stream)
         return out
 
+    def execute_batch(self, acts: Sequence[Sequence[torch.Tensor]], weights: Optional[Sequence[float]] = None,
+                      densities: Optional[Sequence[Optional[torch.Tensor]]] = None, rho_ref: float = 1.0, rho_min: float = 0.1,
+                      rho_cut: float = 0.0, scale: float = 1.0, outs: Optional[Sequence[torch.Tensor]] = None) -> list:
+        """`len(acts)` independent volume sets (acts[b] = the T time-point tensors of volume b, at most MAX_T) through ONE
+        pvd_conv_execute_batch call; same per-volume semantics as execute().  FFT algorithm only."""
+        B = len(acts)
+        T = len(acts[0]) if B else 1
+        if self.info.algo != _capi.ALGO_FFT or T > MAX_T or (B and T < 1):
+            raise ValueError("execute_batch: FFT plans, 1..MAX_T time points per volume")
+        for vol in acts:
+            if len(vol) != T:
+                raise ValueError("every volume of a batch needs the same number of time points")
+            for a in vol:
+                if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous() or tuple(a.shape) != self.shape:
+                    raise ValueError("activity tensors must be contiguous float32 CUDA tensors of the plan shape")
+        if densities is not None:
+            if len(densities) != B:
+                raise ValueError("one density entry (tensor or None) per volume")
+            for d in densities:
+                if d is not None and (d.device != self.device or d.dtype != torch.float32 or not d.is_contiguous()
+                                      or tuple(d.shape) != self.out_shape):
+                    raise ValueError("density must be a contiguous float32 CUDA tensor of the output shape")
+        if outs is None:
+            outs = [torch.empty(self.out_shape, dtype=torch.float32, device=self.device) for _ in range(B)]
+        if len(outs) != B:
+            raise ValueError("one output tensor per volume")
+        with torch.cuda.device(self.device):
+            self.lib.conv_execute_batch(self.handle, [[a.data_ptr() for a in vol] for vol in acts],
+                                        None if weights is None else [float(x) for x in weights],
+                                        None if densities is None else [None if d is None else d.data_ptr() for d in densities],
+                                        rho_ref, rho_min, rho_cut, scale, [o.data_ptr() for o in outs], _stream_ptr(self.device))
+        return list(outs)
+
     def check_device_errors(self) -> None:
         """Synchronise the current stream and raise PvdoseError if a device-side watchdog fired (a TMA tile copy that
         never completed); results of that execute are then invalid.  Tests and smoke() call it after executing."""

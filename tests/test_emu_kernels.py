@@ -293,3 +293,35 @@ def test_algo_selection(lib):
     with pytest.raises(PvdoseError) as e:  # the circular mode exists for cubic kernels only
         lib.plan_create((8, 8, 8), (5, 3, 5), 0, 2)
     assert e.value.code == -5
+
+
+def test_batch_execute_matches_single_calls_and_the_oracle(lib):
+    """pvd_conv_execute_batch (SURVEY section 8b `batch`): B volume sets, per-volume density or none, one call."""
+    from pyvoxeldosimetry_b200._capi import PvdoseError
+
+    rng = np.random.default_rng(11)
+    shape, kshape, B, T = (6, 10, 12), (3, 5, 4), 3, 2
+    p = EmuConv(lib, shape, kshape, 0)
+    k = rng.uniform(0, 1, kshape)
+    p.set_kernel(k)
+    vols = [[np.ascontiguousarray(rng.uniform(0, 1e3, shape), np.float32) for _ in range(T)] for _ in range(B)]
+    dens = [np.ascontiguousarray(rng.uniform(0.2, 2.0, shape), np.float32), None, np.ascontiguousarray(rng.uniform(0.2, 2.0, shape), np.float32)]
+    w = [0.5, 1.5]
+    outs = [np.full(shape, np.nan, np.float32) for _ in range(B)]
+    lib.conv_execute_batch(p.plan, [[a.ctypes.data for a in v] for v in vols], w, [None if d is None else d.ctypes.data for d in dens],
+                           1.0, 0.1, 0.0, 2.0, [o.ctypes.data for o in outs])
+    f = lambda x: np.asarray(x, np.float32).astype(np.float64)
+    for b in range(B):
+        single = p.execute(vols[b], w, dens[b], scale=2.0)
+        assert np.array_equal(outs[b], single)
+        ref = 2.0 * orc.conv_reference(sum(np.float64(np.float32(wi)) * f(a) for wi, a in zip(w, vols[b])), f(np.float32(k)))
+        if dens[b] is not None:
+            ref = orc.density_correct(ref, f(dens[b]))
+        assert orc.rel_err_of_peak(outs[b], ref) <= TOL
+    lib.conv_execute_batch(p.plan, [], None, None, 1.0, 0.1, 0.0, 1.0, [])  # empty batch: nothing to do
+    with pytest.raises(ValueError):
+        lib.conv_execute_batch(p.plan, [[vols[0][0].ctypes.data], [vols[1][0].ctypes.data, vols[1][1].ctypes.data]], None, None, 1.0, 0.1, 0.0, 1.0,
+                               [outs[0].ctypes.data, outs[1].ctypes.data])
+    with pytest.raises(PvdoseError):
+        lib.conv_execute_batch(p.plan, [[vols[0][0].ctypes.data]], None, None, 1.0, 0.1, 0.0, 1.0, [None])
+    p.close()

@@ -232,6 +232,33 @@ def test_pipelined_batch_api_matches_single_calls():
     assert calc.calculate_dose_rate_batch([], (1.0, 1.0, 1.0)) == []
 
 
+def test_plan_batch_execute_matches_single_calls():
+    """ConvPlan.execute_batch -> pvd_conv_execute_batch: one C-ABI call for a list of volume sets (menu size: the persistent,
+    dependent-launch kernels chain across volumes), bit-identical to per-volume execute()."""
+    import torch
+
+    from pyvoxeldosimetry_b200.engine import ConvPlan
+
+    dev = torch.device("cuda:0")
+    shape, ks, B, T = (64, 256, 256), (9, 9, 9), 4, 3
+    g = torch.Generator(device=dev).manual_seed(3)
+    plan = ConvPlan(shape, ks, "reference", dev)
+    k = torch.rand(ks, device=dev, generator=g)
+    plan.set_kernel(k)
+    vols = [[torch.rand(shape, device=dev, generator=g) for _ in range(T)] for _ in range(B)]
+    dens = [torch.rand(shape, device=dev, generator=g) + 0.5 if b % 2 == 0 else None for b in range(B)]
+    w = [0.25, 1.0, 0.5]
+    outs = plan.execute_batch(vols, w, dens, scale=3.0)
+    for b in range(B):
+        single = plan.execute(vols[b], w, dens[b], scale=3.0)
+        assert torch.equal(outs[b], single)
+    acc = sum(np.float64(np.float32(wi)) * a.cpu().numpy().astype(np.float64) for wi, a in zip(w, vols[1]))
+    ref = 3.0 * orc.conv_reference_fast(acc, k.cpu().numpy().astype(np.float64))
+    assert orc.rel_err_of_peak(outs[1].cpu().numpy(), ref) <= 1e-4
+    plan.check_device_errors()
+    plan.close()
+
+
 def test_ct_hu_input_matches_oracle_and_density_route():
     """Density correction from the CT itself (int16 Hounsfield units, converted on the device) equals the route
     through host-side densities and the float64 oracle (conv + HU table + density correction)."""

@@ -217,21 +217,34 @@ __global__ void __launch_bounds__(kCtThreads) ct_prepare_kernel(const CtArgs a, 
     // warp-uniform trip count: every lane of a warp runs the same number of iterations (the votes need all lanes)
     const size_t gstride = (size_t)gridDim.x * blockDim.x;
     const size_t warp_first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
-    for (size_t gbase = warp_first; gbase < ngroups; gbase += gstride) {
+    // Two 4-voxel groups per lane and trip: both 128-bit loads are issued before either group is processed (one load in
+    // flight per thread at 32 resident warps per SM is 16 KB per SM - half of what the HBM latency needs).
+    for (size_t gpair = warp_first; gpair < ngroups; gpair += 2 * gstride) {
+        float hh[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        PVD_UNROLL
+        for (int s = 0; s < 2; ++s) {
+            const size_t gb = gpair + s * gstride;
+            if (gb >= ngroups) break;  // warp-uniform
+            const size_t j0 = 4 * (gb + lane);
+            if (vec && j0 + 4 <= n) {
+                const float4 v = *reinterpret_cast<const float4*>(a.hu + j0);
+                hh[s][0] = v.x;
+                hh[s][1] = v.y;
+                hh[s][2] = v.z;
+                hh[s][3] = v.w;
+            } else {
+                PVD_UNROLL
+                for (int q = 0; q < 4; ++q)
+                    if (j0 + q < n) hh[s][q] = a.hu[j0 + q];
+            }
+        }
+        PVD_UNROLL
+        for (int s = 0; s < 2; ++s) {
+        const size_t gbase = gpair + s * gstride;
+        if (gbase >= ngroups) break;  // warp-uniform: the votes below need all lanes
         const size_t i0 = 4 * (gbase + lane);
         const bool full = vec && i0 + 4 <= n;
-        float h[4] = {0.f, 0.f, 0.f, 0.f};
-        if (full) {
-            const float4 v = *reinterpret_cast<const float4*>(a.hu + i0);
-            h[0] = v.x;
-            h[1] = v.y;
-            h[2] = v.z;
-            h[3] = v.w;
-        } else {
-            PVD_UNROLL
-            for (int q = 0; q < 4; ++q)
-                if (i0 + q < n) h[q] = a.hu[i0 + q];
-        }
+        float* h = hh[s];
         PVD_UNROLL
         for (int q = 0; q < 4; ++q) {
             unsigned metal = __ballot_sync(0xFFFFFFFFu, i0 + q < n && h[q] > a.metal_thr);
@@ -292,6 +305,7 @@ __global__ void __launch_bounds__(kCtThreads) ct_prepare_kernel(const CtArgs a, 
                     if (a.labels) a.labels[i0 + q] = (unsigned char)lab[q];
                 }
         }
+        }  // the two groups of this trip
     }
 }
 
@@ -392,13 +406,23 @@ __global__ void __launch_bounds__(256) dvh_hist_kernel(const float* __restrict__
     }
     const float* __restrict__ ed = use_smem ? s_edges : edges;
     const float inv = (float)bins / __fsub_rn(last, first);
+    // How far (in bins) the float32 guess f can sit from the position the float32 EDGES imply: the guess carries a relative
+    // error below 2^-22 (subtraction, reciprocal, product), an edge is off its ideal place by at most half an ulp of the
+    // larger outer edge.  A voxel whose fractional position is further than that (with a 4x margin) from both ends of its
+    // bin cannot be moved by the edge comparisons - it skips the two shared-memory edge loads (99.9 % of the voxels for
+    // 1000 bins); the rest take the exact path, so the counts stay bit-identical to np.histogram.
+    const float tol_edges = 2.5e-7f * fmaxf(fabsf(first), fabsf(last)) * inv;
     auto take = [&](float x) {
         if (!(x >= first && x <= last)) return;  // NaN doses are dropped, as numpy's `keep` mask does
-        int idx = (int)((x - first) * inv);
-        idx = idx < 0 ? 0 : (idx > bins - 1 ? bins - 1 : idx);
-        // one step to the edge-defined bin: the guess is within +-1 (its relative error is a few 2^-24, bins <= 2^20)
-        if (x < ed[idx]) --idx;
-        else if (idx != bins - 1 && x >= ed[idx + 1]) ++idx;
+        const float f = (x - first) * inv;
+        int idx = (int)f;
+        const float frac = f - (float)idx, tol = fmaf(1e-6f, f, tol_edges);
+        if (!(frac > tol && frac < 1.f - tol) || idx >= bins) {
+            idx = idx < 0 ? 0 : (idx > bins - 1 ? bins - 1 : idx);
+            // one step to the edge-defined bin: the guess is within +-1 (its relative error is a few 2^-24, bins <= 2^20)
+            if (x < ed[idx]) --idx;
+            else if (idx != bins - 1 && x >= ed[idx + 1]) ++idx;
+        }
         if (use_smem) atomicAdd(&s_hist[idx], 1u);
         else atomicAdd(&hist[idx], 1ull);
     };

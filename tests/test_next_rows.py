@@ -283,6 +283,48 @@ def test_emulated_dvh_vs_reference_vectors(emu, gold):
     assert emu.roi_minmax(const.ctypes.data, empty.ctypes.data, False, 10, scratch.ctypes.data)[2] == 0
 
 
+def _edge_hugging_doses(first, last, bins, rng):
+    """Doses on, one ulp below and one ulp above every float32 bin edge, plus uniform filler: the voxels for which the
+    histogram's reciprocal-multiply guess and numpy's edge comparisons could disagree."""
+    edges = np.histogram_bin_edges(np.array([first, last], np.float32), bins=bins).astype(np.float32)
+    pick = edges if bins <= 4096 else edges[rng.integers(0, bins + 1, 4096)]
+    near = np.concatenate([pick, np.nextafter(pick, np.float32(-np.inf)), np.nextafter(pick, np.float32(np.inf))])
+    filler = rng.uniform(first, last, 5000).astype(np.float32)
+    d = np.concatenate([near, filler, np.array([first, last], np.float32)]).astype(np.float32)
+    return np.clip(d, np.float32(first), np.float32(last))
+
+
+DVH_EDGE_CASES = [(0.0, 50.0, 1000), (1000.0, 1001.0, 1000), (-3.0, 7.5, 37), (0.0, 1e-3, 4096), (100.0, 5000.0, 65536), (-1e6, 1e6, 999)]
+
+
+def test_emulated_dvh_edge_hugging_doses_match_numpy(emu):
+    rng = np.random.default_rng(12)
+    for first, last, bins in DVH_EDGE_CASES:
+        d = _edge_hugging_doses(first, last, bins, rng)[:6000]  # the emulator runs one host thread per CUDA thread
+        m = np.ones(d.size, np.uint8)
+        edges = np.histogram_bin_edges(np.array([d.min(), d.max()], np.float32), bins=bins)
+        hist = np.empty(bins, np.uint64)
+        emu.dvh_histogram(d.ctypes.data, m.ctypes.data, False, d.size, edges.ctypes.data, bins, float(edges[0]), float(edges[-1]), hist.ctypes.data)
+        np.testing.assert_array_equal(hist, np.histogram(d, bins=bins)[0], err_msg=str((first, last, bins)))
+
+
+@pytest.mark.gpu
+def test_gpu_dvh_edge_hugging_doses_match_numpy():
+    import torch
+    from pyvoxeldosimetry_b200 import engine
+
+    rng = np.random.default_rng(13)
+    dev = torch.device("cuda:0")
+    for first, last, bins in DVH_EDGE_CASES:
+        d = _edge_hugging_doses(first, last, bins, rng)
+        d = np.concatenate([d, rng.uniform(first, last, 1 << 20).astype(np.float32)]).astype(np.float32)
+        d = np.clip(d, np.float32(first), np.float32(last))
+        edges = np.histogram_bin_edges(np.array([d.min(), d.max()], np.float32), bins=bins)
+        hist = engine.dvh_histogram(torch.from_numpy(d).to(dev), torch.ones(d.size, dtype=torch.uint8, device=dev),
+                                    torch.from_numpy(edges.astype(np.float32)).to(dev))
+        np.testing.assert_array_equal(hist.cpu().numpy().astype(np.int64), np.histogram(d, bins=bins)[0], err_msg=str((first, last, bins)))
+
+
 # ----------------------------------------------------------------------------------------- GPU: product API
 @pytest.mark.gpu
 def test_gpu_fit_api_vs_reference_vectors_and_oracle(gold):

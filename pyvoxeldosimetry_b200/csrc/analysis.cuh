@@ -217,34 +217,21 @@ __global__ void __launch_bounds__(kCtThreads) ct_prepare_kernel(const CtArgs a, 
     // warp-uniform trip count: every lane of a warp runs the same number of iterations (the votes need all lanes)
     const size_t gstride = (size_t)gridDim.x * blockDim.x;
     const size_t warp_first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
-    // Two 4-voxel groups per lane and trip: both 128-bit loads are issued before either group is processed (one load in
-    // flight per thread at 32 resident warps per SM is 16 KB per SM - half of what the HBM latency needs).
-    for (size_t gpair = warp_first; gpair < ngroups; gpair += 2 * gstride) {
-        float hh[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        PVD_UNROLL
-        for (int s = 0; s < 2; ++s) {
-            const size_t gb = gpair + s * gstride;
-            if (gb >= ngroups) break;  // warp-uniform
-            const size_t j0 = 4 * (gb + lane);
-            if (vec && j0 + 4 <= n) {
-                const float4 v = *reinterpret_cast<const float4*>(a.hu + j0);
-                hh[s][0] = v.x;
-                hh[s][1] = v.y;
-                hh[s][2] = v.z;
-                hh[s][3] = v.w;
-            } else {
-                PVD_UNROLL
-                for (int q = 0; q < 4; ++q)
-                    if (j0 + q < n) hh[s][q] = a.hu[j0 + q];
-            }
-        }
-        PVD_UNROLL
-        for (int s = 0; s < 2; ++s) {
-        const size_t gbase = gpair + s * gstride;
-        if (gbase >= ngroups) break;  // warp-uniform: the votes below need all lanes
+    for (size_t gbase = warp_first; gbase < ngroups; gbase += gstride) {
         const size_t i0 = 4 * (gbase + lane);
         const bool full = vec && i0 + 4 <= n;
-        float* h = hh[s];
+        float h[4] = {0.f, 0.f, 0.f, 0.f};
+        if (full) {
+            const float4 v = *reinterpret_cast<const float4*>(a.hu + i0);
+            h[0] = v.x;
+            h[1] = v.y;
+            h[2] = v.z;
+            h[3] = v.w;
+        } else {
+            PVD_UNROLL
+            for (int q = 0; q < 4; ++q)
+                if (i0 + q < n) h[q] = a.hu[i0 + q];
+        }
         PVD_UNROLL
         for (int q = 0; q < 4; ++q) {
             unsigned metal = __ballot_sync(0xFFFFFFFFu, i0 + q < n && h[q] > a.metal_thr);
@@ -305,7 +292,6 @@ __global__ void __launch_bounds__(kCtThreads) ct_prepare_kernel(const CtArgs a, 
                     if (a.labels) a.labels[i0 + q] = (unsigned char)lab[q];
                 }
         }
-        }  // the two groups of this trip
     }
 }
 

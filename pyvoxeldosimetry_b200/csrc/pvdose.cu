@@ -174,12 +174,14 @@ struct FastRows {
 // forward*spectrum*inverse pass keeps the full-line kernel (64-byte accesses at a plane stride waste DRAM pages: measured
 // 0.457 vs 0.262 ms at 512) as a tile walk; prefetching the next tile's lines into L2 from inside the walk made it SLOWER
 // (1024: 3.35 -> 4.18 ms, 1152: 3.70 -> 5.34 ms, profiles/r02_ab_long_columns.jsonl) and is not in the code.
-#define PVD_COLS_HALF(N, NT, NTP, R1, R2, R3)                                                                          \
+#define PVD_COLS_HALF(N, NT, NTP, R1, R2, R3, NTX, X1, X2, X3)                                                         \
     {                                                                                                                  \
-        N, NT, PVD_COLS_FN(N, NT, R1, R2, R3),                                                                         \
+        N, NT,                                                                                                         \
+            {cols_fast_kernel<N, NT, R1, R2, R3, COL_FWD>, cols_fast_kernel<N, NT, R1, R2, R3, COL_INV>,               \
+             cols_fast_kernel<N, NTX, X1, X2, X3, COL_CONV, 1>, cols_fast_kernel<N, NT, R1, R2, R3, COL_SPEC>},        \
             {cols_pipe_kernel<N, NTP, 1, R1, R2, R3, COL_FWD, 8>, cols_pipe_kernel<N, NTP, 1, R1, R2, R3, COL_INV, 8>, \
              nullptr, cols_pipe_kernel<N, NTP, 1, R1, R2, R3, COL_SPEC, 8>},                                           \
-            {NTP, NTP, 0, NTP}, {NT, NT, NT, NT}, 8                                                                    \
+            {NTP, NTP, 0, NTP}, {NT, NT, NTX, NT}, 8                                                                   \
     }
 #define PVD_ROWS(N, NT, MINB, R1, R2, R3)                                                                  \
     {                                                                                                      \
@@ -196,10 +198,10 @@ const FastCols kFastCols[] = {
     PVD_COLS(576, 384, 1, 24, 24, 1),   // 512 + kernel reach ('same' mode of 512-wide volumes)
     PVD_COLS(432, 384, 1, 18, 24, 1),
     PVD_COLS(288, 288, 2, 16, 18, 1),   // 256 + kernel reach
-    PVD_COLS_HALF(1024, 1024, 512, 16, 8, 8),
+    PVD_COLS_HALF(1024, 1024, 512, 16, 8, 8, 512, 32, 32, 1),   // x pass: two radix-32 stages, 512 threads (one exchange per transform)
     // slab decomposition of the 1024 x 1024 x 800 volume ('same' mode): 1024 + reach -> 1152, slabs of
     // 256 / 128 planes + 50 halo planes -> 320 / 180 (192: other kernel sizes)
-    PVD_COLS_HALF(1152, 768, 384, 8, 12, 12),
+    PVD_COLS_HALF(1152, 768, 384, 8, 12, 12, 768, 8, 12, 12),
     PVD_COLS(320, 320, 2, 16, 20, 1),
     PVD_COLS(192, 256, 3, 12, 16, 1),
     PVD_COLS(180, 288, 3, 10, 18, 1),   // 128-plane slab + 50 halo planes = 178 -> 180 (8 ranks; 192 costs 6.7 % more points)

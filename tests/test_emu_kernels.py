@@ -189,6 +189,7 @@ FAST_CASES = [
     ((500, 2, 4), (25, 1, 3), 1, 1, False),    # same mode along x: 500 -> 512, crop offset 12
     ((1152, 2, 4), (5, 1, 2), 0, 1, True),     # slab-decomposition sizes: x <1152> 8*12*12 (one tile per CTA)
     ((2, 320, 6), (1, 7, 2), 0, 1, False),     # y <320> 16*20
+    ((1024, 2, 18), (7, 1, 3), 0, 1, True),    # x <1024>: forward*spectrum*inverse as two radix-32 stages (512 threads)
     ((2, 1024, 20), (1, 5, 3), 0, 1, False),   # y <1024> 16*8*8: persistent kernel on half-line tiles (8 frequencies), 11 frequencies = 1 full + 1 partial tile
     ((3, 1130, 12), (1, 23, 2), 1, 1, True),   # y <1152> 8*12*12 half-line tiles, same mode (rows beyond 1130 zero filled, crop offset 11)
     ((192, 3, 4), (9, 2, 1), 0, 2, True),      # x <192> 12*16 (guarded second stage)

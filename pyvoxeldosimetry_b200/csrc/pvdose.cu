@@ -133,6 +133,7 @@ struct FastRows {
     RowFwdKernelFn fwdPipe;  // persistent cp.async-staged variants (fft_rows_pipe.cuh)
     RowInvKernelFn invPipe;
     size_t smemPipe;
+    int NTinv;               // threads per CTA of the inverse kernels (the two directions may use different radix schedules)
 };
 #define PVD_COLS_FN(N, NT, R1, R2, R3)                                                             \
     {                                                                                                  \
@@ -187,10 +188,20 @@ struct FastRows {
     {                                                                                                      \
         N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>,           \
             rows_fwd_pipe_kernel<N, NT, MINB, R1, R2, R3>, rows_inv_pipe_kernel<N, NT, MINB, R1, R2, R3>,  \
-            (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES + Sched<N, R1, R2, R3>::TOTAL * sizeof(float2) + 16 \
+            (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES + Sched<N, R1, R2, R3>::TOTAL * sizeof(float2) + 16, NT \
+    }
+// separate radix schedules for the forward (NTF threads, F1 F2 F3) and the inverse (NTI threads, I1 I2 I3) direction
+#define PVD_ROWS2(N, NTF, F1, F2, F3, NTI, I1, I2, I3)                                                                   \
+    {                                                                                                                    \
+        N, NTF, rows_fwd_fast_kernel<N, NTF, F1, F2, F3>, rows_inv_fast_kernel<N, NTI, I1, I2, I3>,                      \
+            rows_fwd_pipe_kernel<N, NTF, 1, F1, F2, F3>, rows_inv_pipe_kernel<N, NTI, 1, I1, I2, I3>,                    \
+            (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES +                                                       \
+                (Sched<N, F1, F2, F3>::TOTAL > Sched<N, I1, I2, I3>::TOTAL ? Sched<N, F1, F2, F3>::TOTAL                 \
+                                                                           : Sched<N, I1, I2, I3>::TOTAL) * sizeof(float2) + 16, \
+            NTI                                                                                                          \
     }
 #define PVD_ROWS_NOPIPE(N, NT, R1, R2, R3) \
-    { N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>, nullptr, nullptr, 0 }
+    { N, NT, rows_fwd_fast_kernel<N, NT, R1, R2, R3>, rows_inv_fast_kernel<N, NT, R1, R2, R3>, nullptr, nullptr, 0, NT }
 const FastCols kFastCols[] = {
     PVD_COLS_CX(512, 512, 1, 8, 8, 8, 256, 2, 16, 32, 1),
     PVD_COLS(256, 256, 2, 16, 16, 1),
@@ -212,9 +223,13 @@ const FastRows kFastRows[] = {
     PVD_ROWS(512, 512, 1, 8, 8, 8),
     PVD_ROWS(432, 384, 1, 18, 24, 1),   // 400 + kernel reach
     PVD_ROWS(288, 288, 2, 16, 18, 1),
-    PVD_ROWS(800, 640, 1, 8, 10, 10),          // 1024 x 1024 x 800, reference mode
-    PVD_ROWS(840, 512, 1, 8, 7, 15),           // 800 + kernel reach ('same' mode: 825 points needed): the longest length whose
-                                               // exchange tile + 32-row staging buffer (229.9 KB) still fit one SM, so it runs pipelined
+    // The long rows leave room for ONE CTA per SM, so every block-wide barrier idles the SM: two big-radix stages (one
+    // exchange per transform) beat three small ones wherever the registers hold (profiles/r02_ab_long_rows.jsonl: 800 forward
+    // 1.74 -> 1.42 ms, 840 forward 2.54 -> 1.69 ms, 840 inverse 3.13 -> 2.39 ms per 1024^2 / 1152^2 rows; the 800-point inverse
+    // is faster with three stages, 2.02 vs 2.12 ms).
+    PVD_ROWS2(800, 512, 32, 25, 1, 640, 8, 10, 10),   // 1024 x 1024 x 800, reference mode
+    PVD_ROWS2(840, 480, 30, 28, 1, 480, 28, 30, 1),   // 800 + kernel reach ('same' mode: 825 points needed): the longest length whose
+                                                      // exchange tile + 32-row staging buffer still fit one SM, so it runs pipelined
     PVD_ROWS_NOPIPE(864, 576, 8, 9, 12),       // tile + staging buffer exceed one SM's shared memory
 };
 const FastCols* find_fast_cols(int n) {
@@ -844,7 +859,7 @@ int pvd_plan_set_workspace(pvd_plan* p, void* workspace, size_t bytes, void* str
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->fwdPipe, f->NT, f->smemPipe);
         p->rowPipeGrid[0] = sms * per;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->invPipe, f->NT, f->smemPipe);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, f->invPipe, f->NTinv, f->smemPipe);
         p->rowPipeGrid[1] = sms * per;
     }
     if (PVD_SET_SMEM(rows_fwd_kernel, kMaxSmem) != 0 || PVD_SET_SMEM(rows_inv_kernel, kMaxSmem) != 0 ||
@@ -1157,7 +1172,7 @@ int conv_output(pvd_plan* p, const float* density, float rho_min, float rho_cut,
             }
         }
 #endif
-        PVD_LAUNCH_PDL(p->pdl, f->invPipe, dim3((unsigned)grid), dim3(f->NT), f->smemPipe, stream, a);
+        PVD_LAUNCH_PDL(p->pdl, f->invPipe, dim3((unsigned)grid), dim3(f->NTinv), f->smemPipe, stream, a);
         PVD_CUDA_CHECK("rows_inv_pipe_kernel");
         if (mark) p->mark_end(stream);
         return PVD_OK;
@@ -1165,7 +1180,7 @@ int conv_output(pvd_plan* p, const float* density, float rho_min, float rho_cut,
     if (p->fastRows) {
         const FastRows* f = p->fastRows;
         const size_t smem = ((size_t)f->N * 17 + 4 * f->N) * sizeof(float2);
-        PVD_LAUNCH(f->inv, dim3((unsigned)((nrows + 31) / 32)), dim3(f->NT), smem, stream, a);
+        PVD_LAUNCH(f->inv, dim3((unsigned)((nrows + 31) / 32)), dim3(f->NTinv), smem, stream, a);
         PVD_CUDA_CHECK("rows_inv_fast_kernel");
         if (mark) p->mark_end(stream);
         return PVD_OK;

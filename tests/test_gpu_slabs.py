@@ -171,3 +171,43 @@ def test_two_process_halo_exchange_matches_the_whole_volume(transport):
     assert res["transport"] == transport
     errs = [v for k, v in res.items() if k.startswith("slab_")]
     assert len(errs) == 3 and max(errs) < 1e-5
+
+
+def test_stream_flags_copy_and_reserved_sms_on_one_gpu():
+    """The building blocks of the peer transport on ONE device: a stream-ordered flag write releases a stream-ordered wait,
+    pvd_copy_async copies device memory, and a plan with SMs reserved (smaller persistent grids, plain first launch) gives
+    bit-identical results."""
+    from pyvoxeldosimetry_b200._capi import PvdoseError
+    from pyvoxeldosimetry_b200.engine import ConvPlan, get_lib
+
+    dev = torch.device("cuda:0")
+    lib = get_lib()
+    flags = torch.zeros(4, dtype=torch.int32, device=dev)
+    src = torch.arange(1000, dtype=torch.float32, device=dev)
+    dst = torch.zeros_like(src)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize(dev)
+    with torch.cuda.stream(s2):  # the waiter is enqueued FIRST and must hold the copy back until the flag is raised
+        lib.stream_wait_flag_geq(flags[1:].data_ptr(), 7, s2.cuda_stream)
+        lib.copy_async(dst.data_ptr(), src.data_ptr(), src.numel() * 4, s2.cuda_stream)
+    assert not s2.query()
+    with torch.cuda.stream(s1):
+        lib.stream_write_flag(flags[1:].data_ptr(), 7, s1.cuda_stream)
+    s2.synchronize()
+    assert torch.equal(dst, src) and flags.tolist() == [0, 7, 0, 0]
+    with pytest.raises(PvdoseError):
+        lib.stream_write_flag(0, 1, 0)
+    g = torch.Generator(device=dev).manual_seed(4)
+    shape, ks = (180, 256, 256), (9, 9, 9)
+    plan = ConvPlan(shape, ks, "reference", dev)
+    plan.set_kernel(torch.rand(ks, device=dev, generator=g))
+    a = torch.rand(shape, device=dev, generator=g)
+    ref = plan.execute([a]).clone()
+    lib.plan_reserve_sms(plan.handle, 32)
+    got = plan.execute([a]).clone()
+    lib.plan_reserve_sms(plan.handle, 0)
+    assert torch.equal(ref, got)
+    with pytest.raises(PvdoseError):
+        lib.plan_reserve_sms(plan.handle, 10 ** 6)
+    plan.check_device_errors()
+    plan.close()

@@ -348,7 +348,24 @@ __global__ void roi_minmax_kernel(const float* __restrict__ dose, const M* __res
         ++cnt;
     };
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = gtid; i < n4; i += stride) {
+    size_t i = gtid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 128-bit loads in flight per thread (memory-level parallelism)
+        float4 d[4];
+        bool in[4][4];
+        PVD_UNROLL
+        for (int u = 0; u < 4; ++u) {
+            d[u] = reinterpret_cast<const float4*>(dose)[i + u * stride];
+            load_mask4(mask, i + u * stride, in[u]);
+        }
+        PVD_UNROLL
+        for (int u = 0; u < 4; ++u) {
+            if (in[u][0]) take(d[u].x);
+            if (in[u][1]) take(d[u].y);
+            if (in[u][2]) take(d[u].z);
+            if (in[u][3]) take(d[u].w);
+        }
+    }
+    for (; i < n4; i += stride) {
         const float4 d = reinterpret_cast<const float4*>(dose)[i];
         bool in[4];
         load_mask4(mask, i, in);
@@ -357,8 +374,8 @@ __global__ void roi_minmax_kernel(const float* __restrict__ dose, const M* __res
         if (in[2]) take(d.z);
         if (in[3]) take(d.w);
     }
-    for (size_t i = 4 * n4 + gtid; i < n; i += stride)
-        if (mask[i] > (M)0) take(dose[i]);
+    for (size_t j = 4 * n4 + gtid; j < n; j += stride)
+        if (mask[j] > (M)0) take(dose[j]);
     if (cnt) {
         atomicMin(&s_min, lo);
         atomicMax(&s_max, hi);
@@ -443,6 +460,76 @@ __global__ void __launch_bounds__(256) dvh_hist_kernel(const float* __restrict__
         __syncthreads();
         for (int b = threadIdx.x; b < bins; b += blockDim.x)
             if (s_hist[b]) atomicAdd(&hist[b], (unsigned long long)s_hist[b]);
+    }
+}
+
+// Lane-private variant for <= kDvhLaneBins bins: 32 copies of the histogram, copy l entirely in shared-memory bank l
+// (counter of bin b for lane l at word 32 b + l), so the 32 atomics of a warp never share a bank - with one copy, 32 random
+// bins fall 3-4 deep into some bank and the shared-memory atomics were half of the kernel's time.  One 1024-thread CTA per
+// SM walks the volume; the copies are summed at the end with rotated (conflict-free) reads.  Same bin rule as above.
+constexpr int kDvhLaneBins = 1536;
+constexpr int kDvhLaneThreads = 1024;
+
+template <class M>
+__global__ void __launch_bounds__(kDvhLaneThreads, 1) dvh_hist_lanes_kernel(const float* __restrict__ dose, const M* __restrict__ mask, size_t n,
+                                                                            size_t n4, const float* __restrict__ edges, int bins, float first,
+                                                                            float last, unsigned long long* __restrict__ hist) {
+    PVD_DYN_SMEM(unsigned, sm);
+    unsigned* s_hist = sm;                                              // [bins][32]
+    float* ed = reinterpret_cast<float*>(sm + (size_t)bins * 32);       // [bins + 1]
+    for (int b = threadIdx.x; b < bins * 32; b += blockDim.x) s_hist[b] = 0u;
+    for (int b = threadIdx.x; b <= bins; b += blockDim.x) ed[b] = edges[b];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const float inv = (float)bins / __fsub_rn(last, first);
+    const float tol_edges = 2.5e-7f * fmaxf(fabsf(first), fabsf(last)) * inv;
+    auto take = [&](float x) {
+        if (!(x >= first && x <= last)) return;
+        const float f = (x - first) * inv;
+        int idx = (int)f;
+        const float frac = f - (float)idx, tol = fmaf(1e-6f, f, tol_edges);
+        if (!(frac > tol && frac < 1.f - tol) || idx >= bins) {
+            idx = idx < 0 ? 0 : (idx > bins - 1 ? bins - 1 : idx);
+            if (x < ed[idx]) --idx;
+            else if (idx != bins - 1 && x >= ed[idx + 1]) ++idx;
+        }
+        atomicAdd(&s_hist[idx * 32 + lane], 1u);
+    };
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = gtid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 128-bit loads in flight per thread
+        float4 d[4];
+        bool in[4][4];
+        PVD_UNROLL
+        for (int u = 0; u < 4; ++u) {
+            d[u] = reinterpret_cast<const float4*>(dose)[i + u * stride];
+            load_mask4(mask, i + u * stride, in[u]);
+        }
+        PVD_UNROLL
+        for (int u = 0; u < 4; ++u) {
+            if (in[u][0]) take(d[u].x);
+            if (in[u][1]) take(d[u].y);
+            if (in[u][2]) take(d[u].z);
+            if (in[u][3]) take(d[u].w);
+        }
+    }
+    for (; i < n4; i += stride) {
+        const float4 d = reinterpret_cast<const float4*>(dose)[i];
+        bool in[4];
+        load_mask4(mask, i, in);
+        if (in[0]) take(d.x);
+        if (in[1]) take(d.y);
+        if (in[2]) take(d.z);
+        if (in[3]) take(d.w);
+    }
+    for (size_t j = 4 * n4 + gtid; j < n; j += stride)
+        if (mask[j] > (M)0) take(dose[j]);
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+        unsigned long long c = 0;
+        PVD_UNROLL
+        for (int l = 0; l < 32; ++l) c += s_hist[b * 32 + ((l + lane) & 31)];
+        if (c) atomicAdd(&hist[b], c);
     }
 }
 

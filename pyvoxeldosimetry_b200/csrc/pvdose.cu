@@ -1502,6 +1502,34 @@ int pvd_dvh_histogram(const float* dose, const void* mask, int mask_is_f32, size
     if (cudaMemsetAsync(d_hist, 0, (size_t)bins * sizeof(unsigned long long), st) != cudaSuccess) return fail(PVD_ERR_CUDA, "cudaMemsetAsync failed");
     if (n == 0) return PVD_OK;
     const size_t n4 = dvh_vec_groups(dose, mask, mask_is_f32, n);
+#ifndef PVD_EMULATE
+    const size_t lanes_min_n = (size_t)1 << 22;  // lane-private bins: one 1024-thread CTA per SM (large volumes)
+    const int lanes_threads = kDvhLaneThreads;
+#else
+    const size_t lanes_min_n = 2048;             // the emulator runs one host thread per CUDA thread
+    const int lanes_threads = 64;
+#endif
+    if (bins <= kDvhLaneBins && n >= lanes_min_n) {
+        const size_t smem = ((size_t)bins * 32 + bins + 1) * sizeof(unsigned);
+        int sms = 2;
+#ifndef PVD_EMULATE
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#endif
+        if (mask_is_f32) {
+            if (PVD_SET_SMEM(dvh_hist_lanes_kernel<float>, smem) != 0) return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (dvh)");
+            PVD_LAUNCH(dvh_hist_lanes_kernel<float>, dim3((unsigned)sms), dim3(lanes_threads), smem, st, dose, (const float*)mask, n, n4,
+                       d_edges, bins, first_edge, last_edge, d_hist);
+        } else {
+            if (PVD_SET_SMEM(dvh_hist_lanes_kernel<unsigned char>, smem) != 0)
+                return fail(PVD_ERR_CUDA, "cannot opt in to large shared memory (dvh)");
+            PVD_LAUNCH(dvh_hist_lanes_kernel<unsigned char>, dim3((unsigned)sms), dim3(lanes_threads), smem, st, dose,
+                       (const unsigned char*)mask, n, n4, d_edges, bins, first_edge, last_edge, d_hist);
+        }
+        PVD_CUDA_CHECK("dvh_hist_lanes_kernel");
+        return PVD_OK;
+    }
     if (mask_is_f32)
         PVD_LAUNCH(dvh_hist_kernel<float>, dim3(ew_grid(n / 4 + 1)), dim3(256), 0, st, dose, (const float*)mask, n, n4, d_edges,
                    bins, first_edge, last_edge, d_hist);

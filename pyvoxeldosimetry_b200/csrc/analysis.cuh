@@ -192,6 +192,15 @@ struct CtArgs {
     float rho0, seg_hu[31], seg_len[31], seg_slope[31];
     int nr;
     float lo[8], hi[8];
+    // Merged interval table (built on the host, pvd_ct_prepare): the density knots, every range start lo_c and the float
+    // after every range end hi_c, sorted, cut the HU axis into intervals on which the density is ONE linear piece and the
+    // class mask is constant.  thr[] = the sorted cuts padded with +inf to 2^lut_log - 1 entries; entry k (k = number of
+    // cuts <= h, found by a branch-free binary search in shared memory: the tables are a few dozen words, so 32 different
+    // HU values read different banks) = (a, rho(a), slope, mask bits): rho(h) = rho(a) + slope (h - a).
+    int lut_log;  // 0: table too large, use the sums above
+    float knot_lo, knot_hi;  // first / last density knot
+    float thr[63];
+    float ent[64][4];
     float* corrected;
     float* rho;
     unsigned char* labels;
@@ -204,34 +213,67 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // scipy 'reflect': 
 
 constexpr int kCtThreads = 256;
 
+__device__ __forceinline__ float4 ct_ld128(const float* p) {
+#ifdef PVD_EMULATE
+    return *reinterpret_cast<const float4*>(p);
+#else
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
+
 // Streaming pass, four consecutive voxels per thread (128-bit loads / stores when the volume is 16-byte aligned), no
 // block-wide synchronisation.  Metal voxels are rare, so their 9^3 gathers are not done by the owning lane alone
 // (it would run 729 taps while 31 lanes idle): the warp votes, and for every metal voxel found all 32 lanes share
 // the work - the 81 (dx, dy) columns of 9 contiguous z taps are dealt round-robin over the lanes and the partial
 // sums are combined with a butterfly of shuffles (fixed order: deterministic result).
-template <bool SEG8>  // SEG8: at most 8 density segments, padded with zero slopes -> fully unrolled, constants as operands
+template <int LOG>  // LOG > 0: merged interval table of 2^LOG entries in shared memory; 0: direct sums over segments and ranges
 __global__ void __launch_bounds__(kCtThreads) ct_prepare_kernel(const CtArgs a, const int vec) {
+    __shared__ float s_thr[LOG > 0 ? (1 << LOG) : 1];
+    __shared__ float4 s_ent[LOG > 0 ? (1 << LOG) : 1];
+    if constexpr (LOG > 0) {
+        for (int i = threadIdx.x; i < (1 << LOG); i += blockDim.x) {
+            s_thr[i] = i < (1 << LOG) - 1 ? a.thr[i] : 0.f;
+            s_ent[i] = make_float4(a.ent[i][0], a.ent[i][1], a.ent[i][2], a.ent[i][3]);
+        }
+        __syncthreads();
+    }
     const size_t n = (size_t)a.n0 * a.n1 * a.n2;
     const size_t ngroups = (n + 3) / 4;
     const int lane = threadIdx.x & 31;
     // warp-uniform trip count: every lane of a warp runs the same number of iterations (the votes need all lanes)
     const size_t gstride = (size_t)gridDim.x * blockDim.x;
     const size_t warp_first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
-    for (size_t gbase = warp_first; gbase < ngroups; gbase += gstride) {
-        const size_t i0 = 4 * (gbase + lane);
-        const bool full = vec && i0 + 4 <= n;
-        float h[4] = {0.f, 0.f, 0.f, 0.f};
-        if (full) {
-            const float4 v = *reinterpret_cast<const float4*>(a.hu + i0);
-            h[0] = v.x;
-            h[1] = v.y;
-            h[2] = v.z;
-            h[3] = v.w;
+    // Software pipeline: the 128-bit load of the NEXT trip's group is issued before this trip's ~260 instructions of table
+    // arithmetic, so every warp always has a load in flight (one load per thread and trip left the pass at 38 % of its
+    // issue slots with 16 KB per SM in flight).  The loads are volatile asm so the compiler keeps them where they are.
+    auto fetch = [&](size_t gb, float (&hv)[4]) {
+        hv[0] = hv[1] = hv[2] = hv[3] = 0.f;
+        if (gb >= ngroups) return;
+        const size_t j0 = 4 * (gb + lane);
+        if (vec && j0 + 4 <= n) {
+            const float4 v = ct_ld128(a.hu + j0);
+            hv[0] = v.x;
+            hv[1] = v.y;
+            hv[2] = v.z;
+            hv[3] = v.w;
         } else {
             PVD_UNROLL
             for (int q = 0; q < 4; ++q)
-                if (i0 + q < n) h[q] = a.hu[i0 + q];
+                if (j0 + q < n) hv[q] = a.hu[j0 + q];
         }
+    };
+    float hn[4];
+    fetch(warp_first, hn);
+    for (size_t gbase = warp_first; gbase < ngroups; gbase += gstride) {
+        const size_t i0 = 4 * (gbase + lane);
+        const bool full = vec && i0 + 4 <= n;
+        float h[4] = {hn[0], hn[1], hn[2], hn[3]};
+        fetch(gbase + gstride, hn);
+        // metal voxels are rare: ONE vote over the four voxels of every lane decides whether the warp looks closer
+        const bool any_metal = __any_sync(0xFFFFFFFFu, fmaxf(fmaxf(h[0], h[1]), fmaxf(h[2], h[3])) > a.metal_thr);
+        if (any_metal) {
         PVD_UNROLL
         for (int q = 0; q < 4; ++q) {
             unsigned metal = __ballot_sync(0xFFFFFFFFu, i0 + q < n && h[q] > a.metal_thr);
@@ -262,22 +304,28 @@ __global__ void __launch_bounds__(kCtThreads) ct_prepare_kernel(const CtArgs a, 
                 if (lane == owner) h[q] = part;
             }
         }
+        }
         float rr[4];
         unsigned lab[4];
         PVD_UNROLL
         for (int q = 0; q < 4; ++q) {
-            float acc = a.rho0;
-            if (SEG8) {
+            if constexpr (LOG > 0) {
+                int pos = 0;  // number of cuts <= h (NaN: 0 -> the entry below every cut: rho of the first knot, no class)
                 PVD_UNROLL
-                for (int j = 0; j < 8; ++j) acc = fmaf(a.seg_slope[j], fminf(fmaxf(h[q] - a.seg_hu[j], 0.f), a.seg_len[j]), acc);
+                for (int st = 1 << (LOG - 1); st > 0; st >>= 1) pos += (s_thr[pos + st - 1] <= h[q]) ? st : 0;
+                const float4 e = s_ent[pos];
+                // h clamped to the knot range for the linear piece: beyond it the slope is 0 and 0 * inf would be NaN
+                rr[q] = fmaf(e.z, fminf(fmaxf(h[q], a.knot_lo), a.knot_hi) - e.x, e.y);
+                lab[q] = __float_as_uint(e.w);
             } else {
+                float acc = a.rho0;
                 for (int j = 0; j < a.nseg; ++j) acc = fmaf(a.seg_slope[j], fminf(fmaxf(h[q] - a.seg_hu[j], 0.f), a.seg_len[j]), acc);
+                rr[q] = acc;
+                unsigned m = 0;
+                PVD_UNROLL
+                for (int c = 0; c < 8; ++c) m |= (h[q] >= a.lo[c] && h[q] <= a.hi[c]) ? (1u << c) : 0u;  // unused ranges are empty (lo > hi)
+                lab[q] = m;
             }
-            rr[q] = acc;
-            unsigned m = 0;
-            PVD_UNROLL
-            for (int c = 0; c < 8; ++c) m |= (h[q] >= a.lo[c] && h[q] <= a.hi[c]) ? (1u << c) : 0u;  // unused ranges are empty (lo > hi)
-            lab[q] = m;
         }
         if (full) {
             if (a.corrected) *reinterpret_cast<float4*>(a.corrected + i0) = make_float4(h[0], h[1], h[2], h[3]);

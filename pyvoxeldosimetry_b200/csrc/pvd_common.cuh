@@ -74,6 +74,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     c.warp_bar->arrive_and_wait();
     return m;
 }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
     unsigned u;
     std::memcpy(&u, &v, 4);

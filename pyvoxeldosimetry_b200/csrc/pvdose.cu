@@ -1446,10 +1446,61 @@ int pvd_ct_prepare(const float* hu, const int n[3], float metal_threshold, const
     const size_t nv = (size_t)n[0] * n[1] * n[2];
     const int vec = (((uintptr_t)hu | (uintptr_t)corrected | (uintptr_t)rho) & 15) == 0 && ((uintptr_t)labels & 3) == 0;
     const unsigned grid = (unsigned)std::min<size_t>((nv + 4 * kCtThreads - 1) / (4 * kCtThreads), 148 * 8);
-    if (a.nseg <= 8)
-        PVD_LAUNCH(ct_prepare_kernel<true>, dim3(grid), dim3(kCtThreads), 0, (cudaStream_t)stream, a, vec);
+    // merged interval table: cuts = density knots + range starts + the float after every range end
+    {
+        std::vector<float> cuts;
+        Knots k;
+        k.nk = 0;
+        if (rho) {
+            fill_knots(h_knots, nk, k);
+            for (int j = 0; j < nk; ++j) cuts.push_back(k.hu[j]);
+            a.knot_lo = k.hu[0];
+            a.knot_hi = k.hu[nk - 1];
+        }
+        for (int c = 0; c < a.nr; ++c)
+            if (a.lo[c] <= a.hi[c]) {
+                cuts.push_back(a.lo[c]);
+                if (a.hi[c] < INFINITY) cuts.push_back(std::nextafterf(a.hi[c], INFINITY));
+            }
+        std::sort(cuts.begin(), cuts.end());
+        cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+        const int m = (int)cuts.size();
+        a.lut_log = m <= 31 ? 5 : (m <= 63 ? 6 : 0);
+        bool finite = true;
+        for (float c : cuts) finite = finite && !std::isnan(c);
+        if (!finite) a.lut_log = 0;
+        if (a.lut_log) {
+            const int slots = (1 << a.lut_log) - 1;
+            for (int i = 0; i < slots; ++i) a.thr[i] = i < m ? cuts[i] : INFINITY;
+            for (int e = 0; e <= m; ++e) {
+                // a representative of the interval: its first value (entry 0 = below every cut / NaN: first knot, no class)
+                const float r = e == 0 ? -INFINITY : cuts[e - 1];
+                float a0 = 0.f, r0 = 0.f, sl = 0.f;
+                if (k.nk) {
+                    int j = 0;
+                    while (j + 1 < k.nk && r >= k.hu[j + 1]) ++j;
+                    a0 = k.hu[j];
+                    r0 = k.rho[j];
+                    if (r >= k.hu[0] && j + 1 < k.nk) sl = (k.rho[j + 1] - k.rho[j]) / (k.hu[j + 1] - k.hu[j]);
+                }
+                unsigned mask = 0;
+                if (e > 0)
+                    for (int c = 0; c < a.nr; ++c)
+                        if (r >= a.lo[c] && r <= a.hi[c]) mask |= 1u << c;
+                a.ent[e][0] = a0;
+                a.ent[e][1] = r0;
+                a.ent[e][2] = sl;
+                memcpy(&a.ent[e][3], &mask, 4);
+            }
+            for (int e = m + 1; e < (1 << a.lut_log); ++e) memcpy(a.ent[e], a.ent[m], sizeof a.ent[e]);
+        }
+    }
+    if (a.lut_log == 5)
+        PVD_LAUNCH(ct_prepare_kernel<5>, dim3(grid), dim3(kCtThreads), 0, (cudaStream_t)stream, a, vec);
+    else if (a.lut_log == 6)
+        PVD_LAUNCH(ct_prepare_kernel<6>, dim3(grid), dim3(kCtThreads), 0, (cudaStream_t)stream, a, vec);
     else
-        PVD_LAUNCH(ct_prepare_kernel<false>, dim3(grid), dim3(kCtThreads), 0, (cudaStream_t)stream, a, vec);
+        PVD_LAUNCH(ct_prepare_kernel<0>, dim3(grid), dim3(kCtThreads), 0, (cudaStream_t)stream, a, vec);
     PVD_CUDA_CHECK("ct_prepare_kernel");
     return PVD_OK;
 }

@@ -224,6 +224,44 @@ def test_emulated_ct_prepare_vs_reference_vectors(emu, gold):
     np.testing.assert_allclose(out, orc.handle_artifacts(t), atol=1e-3)
 
 
+def _ct_boundary_case(rng):
+    """HU values on, one ulp below and one ulp above every range end and every density knot (+ NaN, +-inf, filler), with
+    overlapping, touching, single-point, empty and half-infinite class ranges: what the merged interval table must get right."""
+    knots = [(-1000.0, 0.00129), (-700.0, 0.26), (-100.0, 0.92), (0.0, 1.0), (40.0, 1.05), (350.0, 1.42), (1200.0, 1.92), (3000.0, 2.9)]
+    ranges = [(-1000.0, -700.0), (-700.0, -100.0), (-150.0, 40.0), (40.0, 40.0), (41.0, 350.0), (300.0, float("inf")), (10.0, -10.0),
+              (-float("inf"), -900.0)]
+    pts = np.array([v for lo_hi in ranges for v in lo_hi if np.isfinite(v)] + [k[0] for k in knots], np.float32)
+    near = np.concatenate([pts, np.nextafter(pts, np.float32(-np.inf)), np.nextafter(pts, np.float32(np.inf))])
+    hu = np.concatenate([near, rng.uniform(-1500, 3500, 997).astype(np.float32),
+                         np.array([np.nan, np.inf, -np.inf, 0.0, -0.0], np.float32)]).astype(np.float32)
+    hu = np.concatenate([hu, np.zeros((-hu.size) % 4, np.float32)]).reshape(1, -1, 4)
+    h64 = hu.astype(np.float64)
+    lab = np.zeros(hu.shape, np.uint8)
+    for c, (lo, hi) in enumerate(ranges):
+        with np.errstate(invalid="ignore"):
+            lab |= ((hu >= np.float32(lo)) & (hu <= np.float32(hi))).astype(np.uint8) << c
+    kx, ky = np.array(knots).T
+    rho = np.interp(h64, kx, ky)
+    rho[np.isnan(h64)] = ky[0]  # a NaN voxel gets the first knot's density and no class (as the sum form did)
+    return hu, knots, ranges, lab, rho
+
+
+def test_emulated_ct_prepare_interval_table_boundaries(emu):
+    hu, knots, ranges, lab, rho = _ct_boundary_case(np.random.default_rng(21))
+    r, l = np.empty_like(hu), np.empty(hu.shape, np.uint8)
+    emu.ct_prepare(hu.ctypes.data, hu.shape, float("inf"), knots, ranges, None, r.ctypes.data, l.ctypes.data)
+    np.testing.assert_array_equal(l, lab)
+    np.testing.assert_allclose(r, rho, rtol=3e-6, atol=1e-7)
+    # > 31 cuts (12 knots + 8 ranges with distinct ends = up to 28; 24 knots + ranges -> the 64-entry table)
+    knots24 = [(-1000.0 + 150.0 * j, 0.001 + 0.1 * j + 0.004 * j * j) for j in range(24)]
+    emu.ct_prepare(hu.ctypes.data, hu.shape, float("inf"), knots24, ranges, None, r.ctypes.data, l.ctypes.data)
+    kx, ky = np.array(knots24).T
+    want = np.interp(hu.astype(np.float64), kx, ky)
+    want[np.isnan(hu)] = ky[0]
+    np.testing.assert_array_equal(l, lab)
+    np.testing.assert_allclose(r, want, rtol=3e-6, atol=1e-7)
+
+
 def _check_dvh(gold, fn):
     dose, mask = gold["dvh|dose"], gold["dvh|mask"]
     for bins in (1000, 17):
@@ -454,3 +492,15 @@ def test_nifti_header_bytes_match_the_nifti1_struct(tmp_path):
     # voxel data: Fortran order float32 right at vox_offset
     data = np.frombuffer(content, "<f4", count=dose.size, offset=352 + esize).reshape(dose.shape, order="F")
     assert np.array_equal(data, dose)
+
+
+@pytest.mark.gpu
+def test_gpu_ct_prepare_interval_table_boundaries():
+    import torch
+    from pyvoxeldosimetry_b200 import engine
+
+    hu, knots, ranges, lab, rho = _ct_boundary_case(np.random.default_rng(22))
+    big = np.tile(hu, (64, 1, 1))  # enough groups for several warps per block
+    _, r, l = engine.ct_prepare(torch.from_numpy(big).cuda(), float("inf"), knots, ranges, want_corrected=False)
+    np.testing.assert_array_equal(l.cpu().numpy(), np.tile(lab, (64, 1, 1)))
+    np.testing.assert_allclose(r.cpu().numpy(), np.tile(rho, (64, 1, 1)), rtol=3e-6, atol=1e-7)

@@ -208,14 +208,18 @@ const FastCols kFastCols[] = {
     PVD_COLS(400, 320, 1, 20, 20, 1),
     PVD_COLS(576, 384, 1, 24, 24, 1),   // 512 + kernel reach ('same' mode of 512-wide volumes)
     PVD_COLS(432, 384, 1, 18, 24, 1),
-    PVD_COLS(288, 288, 2, 16, 18, 1),   // 256 + kernel reach
+    PVD_COLS_CX(288, 288, 2, 16, 18, 1, 288, 2, 16, 18, 1),   // 256 + kernel reach; x pass as at 320 / 180 below (0.081 -> 0.074 ms)
     PVD_COLS_HALF(1024, 1024, 512, 16, 8, 8, 512, 32, 32, 1),   // x pass: two radix-32 stages, 512 threads (one exchange per transform)
     // slab decomposition of the 1024 x 1024 x 800 volume ('same' mode): 1024 + reach -> 1152, slabs of
     // 256 / 128 planes + 50 halo planes -> 320 / 180 (192: other kernel sizes)
     PVD_COLS_HALF(1152, 768, 384, 8, 12, 12, 768, 8, 12, 12),
-    PVD_COLS(320, 320, 2, 16, 20, 1),
+    // x pass of the slab plans as the one-tile-per-CTA walk at 2 CTAs per SM (as at 512): the persistent pipelined form of the
+    // forward*spectrum*inverse kernel spilled at these lengths (320: 324 B, 180: 276 B) - per 4-rank slab 0.898 -> 0.659 ms,
+    // per 8-rank slab 0.485 -> 0.439 ms (profiles/r02_ab_slab_x_pass.jsonl)
+    PVD_COLS_CX(320, 320, 2, 16, 20, 1, 320, 2, 16, 20, 1),
     PVD_COLS(192, 256, 3, 12, 16, 1),
-    PVD_COLS(180, 288, 3, 10, 18, 1),   // 128-plane slab + 50 halo planes = 178 -> 180 (8 ranks; 192 costs 6.7 % more points)
+    // 128-plane slab + 50 halo planes = 178 -> 180 (8 ranks; 192 costs 6.7 % more points)
+    PVD_COLS_CX(180, 288, 3, 10, 18, 1, 288, 2, 10, 18, 1),
 };
 const FastRows kFastRows[] = {
     PVD_ROWS(400, 320, 2, 20, 20, 1),

@@ -16,6 +16,7 @@ CASES = {
     'c3': ((512, 512, 400), (51, 51, 51), 'reference', 1, True),
     'c3same': ((512, 512, 400), (51, 51, 51), 'same', 1, True),
     'c2': ((256, 256, 256), (31, 31, 31), 'reference', 4, False),
+    'c2same': ((256, 256, 256), (31, 31, 31), 'same', 4, False),
     'c5slab': ((306, 1024, 800), (51, 51, 51), 'reference', 1, True),
     'c5': ((1024, 1024, 800), (51, 51, 51), 'reference', 1, True),
     'c5same': ((1024, 1024, 800), (51, 51, 51), 'same', 1, True),

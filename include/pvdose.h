@@ -233,6 +233,16 @@ int pvd_i16_to_f32(const void* d_in, int is_unsigned, float slope, float interce
  * integrate_dose_rates (core/dose_calculator.py:138): out = sum_t h_weights[t] * vol[t]. T <= 16. ---- */
 int pvd_weighted_sum(const float* const* h_vol, const float* h_weights, int T, float* out, size_t n, void* stream);
 
+/* ---- interpolate_timepoints (core/utils.py:154-191) and every other fixed linear combination of the sampled volumes:
+ * out[j] = sum_t h_W[j * T + t] * vol[t], j < J <= 16, T <= 16, in ONE pass (each volume read once, each output written
+ * once).  scipy's interp1d of kind 'linear' / 'cubic' / 'previous' - what the reference calls - is linear in the sampled
+ * volumes with weights that depend on the time points only; the host computes them
+ * (pyvoxeldosimetry_b200.core.utils.interpolation_weights).  A zero weight skips the product (the volume is not even
+ * loaded when no output uses it), a NaN weight yields NaN ('previous' before the first sample).  h_W NULL = all ones.
+ * An output may BE one of the inputs (same pointer: every thread reads its voxels of all volumes before it writes them);
+ * partial overlap is not allowed.  pvd_weighted_sum is the J = 1 case. ---- */
+int pvd_weighted_combine(const float* const* h_vol, int T, const float* h_W, float* const* h_out, int J, size_t n, void* stream);
+
 /* ---- A11: TimeCurveFitting._calculate_accumulated_dose (time_integration/curve_fitting.py:74-84):
  * out = A0 / lambda * (1 - exp(-lambda * t_limit)) elementwise. ---- */
 int pvd_monoexp_integral(const float* A0, const float* lambda, float t_limit, float* out, size_t n, void* stream);

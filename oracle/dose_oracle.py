@@ -487,6 +487,71 @@ def load_kernel_dat(filename):
 # --------------------------------------------------------------------------------------
 
 
+# --------------------------------------------------------------------------------------
+# interpolate_timepoints   core/utils.py:154-191
+# The arithmetic lives in scipy.interpolate.interp1d (third party, not vendored; the reference pins
+# `scipy>=1.6.0`, here scipy 1.18.1).  Restated from its published algorithm: sort by x (stable), then
+#   linear    y = (x_new - x_lo)/(x_hi - x_lo) * y_hi + (x_hi - x_new)/(x_hi - x_lo) * y_lo on the bracketing pair
+#             (searchsorted, clipped to [1, n-1]: the end segments extrapolate);
+#   previous  the last sample at or before x_new; NaN before the first sample, the last sample beyond the end
+#             (what interp1d does for fill_value='extrapolate');
+#   cubic     the not-a-knot cubic spline through all samples (make_interp_spline(k=3) default), extended
+#             beyond the ends by its end polynomials.
+# Pinned by oracle/gen_golden.py against the real reference function (tests/golden/interp_ref.npz): linear and
+# previous bit for bit, cubic to 1e-12 relative (a different but equivalent linear solve).
+# --------------------------------------------------------------------------------------
+
+
+def _notaknot_second_derivatives(x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """Second derivatives M_i at the samples of the C2 piecewise cubic through (x_i, y_i[...]) whose third derivative is
+    continuous at x_1 and x_{n-2} (not-a-knot).  y has shape (n, ...)."""
+    n = len(x)
+    h = np.diff(x)
+    A = np.zeros((n, n))
+    rhs = np.zeros((n,) + y.shape[1:])
+    for i in range(1, n - 1):  # continuity of the first derivative at the interior samples
+        A[i, i - 1], A[i, i], A[i, i + 1] = h[i - 1] / 6, (h[i - 1] + h[i]) / 3, h[i] / 6
+        rhs[i] = (y[i + 1] - y[i]) / h[i] - (y[i] - y[i - 1]) / h[i - 1]
+    # third derivative (M_{i+1} - M_i)/h_i continuous at x_1 and x_{n-2}
+    A[0, 0], A[0, 1], A[0, 2] = h[1], -(h[0] + h[1]), h[0]
+    A[n - 1, n - 3], A[n - 1, n - 2], A[n - 1, n - 1] = h[n - 2], -(h[n - 3] + h[n - 2]), h[n - 3]
+    return np.linalg.solve(A, rhs.reshape(n, -1)).reshape(rhs.shape)
+
+
+def interpolate_timepoints(time_points: Sequence[float], values: Sequence[np.ndarray], new_times: Sequence[float],
+                           method: str = "linear") -> List[np.ndarray]:
+    """core/utils.py:154-191: the sampled 3-D arrays interpolated voxel by voxel along time."""
+    if len(time_points) != len(values):
+        raise ValueError("Number of time points must match number of values")
+    shape = np.asarray(values[0]).shape
+    x = np.asarray(time_points, dtype=np.float64)
+    y = np.array([np.asarray(v, dtype=np.float64).reshape(-1) for v in values])
+    order = np.argsort(x, kind="mergesort")
+    x, y = x[order], y[order]
+    xn = np.asarray(new_times, dtype=np.float64)
+    n = len(x)
+    if method == "linear":
+        hi = np.searchsorted(x, xn).clip(1, n - 1).astype(int)
+        lo = hi - 1
+        out = ((xn - x[lo]) / (x[hi] - x[lo]))[:, None] * y[hi] + ((x[hi] - xn) / (x[hi] - x[lo]))[:, None] * y[lo]
+    elif method == "previous":
+        idx = np.searchsorted(np.nextafter(x, -np.inf), xn, side="left").clip(1, n).astype(int)
+        out = y[idx - 1].copy()
+        out[xn < x[0]] = np.nan
+        out[xn > x[-1]] = y[-1]
+    elif method == "cubic":
+        if n < 4:
+            raise ValueError("x and y arrays must have at least 4 entries")
+        M = _notaknot_second_derivatives(x, y)
+        seg = (np.searchsorted(x, xn, side="right") - 1).clip(0, n - 2)  # beyond the ends: the end polynomials
+        h = (x[seg + 1] - x[seg])[:, None]
+        a, b = (x[seg + 1] - xn)[:, None], (xn - x[seg])[:, None]
+        out = (M[seg] * a ** 3 + M[seg + 1] * b ** 3) / (6 * h) + (y[seg] / h - M[seg] * h / 6) * a + (y[seg + 1] / h - M[seg + 1] * h / 6) * b
+    else:
+        raise NotImplementedError(f"{method} is not restated")
+    return [v.reshape(shape) for v in out]
+
+
 def sphere_activity(size=(48, 48, 48), center=(24, 24, 24), radius=8, activity=2e6) -> np.ndarray:
     """examples/single_timepoint_y90_physical_decay.py:14-21 (vectorised, same voxels)."""
     x, y, z = np.ogrid[: size[0], : size[1], : size[2]]

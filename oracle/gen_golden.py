@@ -114,6 +114,29 @@ def gen_next_rows(orc):
     np.savez_compressed(os.path.join(OUT, "next_ref.npz"), **out)
 
 
+def gen_interp(orc):
+    """interpolate_timepoints (core/utils.py:154-191) run through the REAL reference (scipy interp1d underneath): unsorted
+    and non-uniform time points, new times inside, on and beyond the sampled range, the three kinds the docstring names."""
+    from pyvoxeldosimetry.core import utils as ref_utils
+
+    rng = np.random.default_rng(154191)
+    out = {}
+    for name, times, shape in (("s5", [24.0, 4.0, 96.0, 168.0, 48.0], (4, 3, 5)), ("s4", [1.0, 3.0, 7.5, 20.0], (2, 3, 4)),
+                               ("s7", [0.0, 1.0, 2.0, 4.0, 8.0, 16.0, 32.0], (3, 2, 2))):
+        vals = [rng.uniform(0.0, 1e4, shape) * np.exp(-0.01 * t) for t in times]
+        new = [min(times) - 3.0, times[0], 5.5, 30.0, max(times), max(times) + 50.0, min(times), 6.0]
+        out[name + "|times"], out[name + "|values"], out[name + "|new"] = np.array(times), np.stack(vals), np.array(new)
+        for method in ("linear", "cubic", "previous"):
+            ref = np.stack(ref_utils.interpolate_timepoints(times, vals, new, method))
+            mine = np.stack(orc.interpolate_timepoints(times, vals, new, method))
+            if method == "cubic":
+                assert np.allclose(mine, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max()), (name, method)
+            else:
+                assert np.array_equal(mine, ref, equal_nan=True), (name, method)
+            out[f"{name}|{method}"] = ref
+    np.savez_compressed(os.path.join(OUT, "interp_ref.npz"), **out)
+
+
 def main():
     tmp = import_reference()
     sys.path.insert(0, REPO)
@@ -234,6 +257,7 @@ def main():
     # keep three orthogonal central planes through the peak (8,8,8) as array fixtures (small)
     np.savez_compressed(os.path.join(OUT, "c1_ref.npz"), plane_x8=d1[8], plane_y8=d1[:, 8], plane_z8=d1[:, :, 8])
     gen_next_rows(orc)
+    gen_interp(orc)
     with open(os.path.join(OUT, "kats.json"), "w") as f:
         json.dump({k: float(v) for k, v in kats.items()}, f, indent=1, sort_keys=True)
     print("golden written to", OUT)

@@ -23,7 +23,7 @@ MAX_T = 16
 SYMBOLS = [
     "pvd_version", "pvd_build_id", "pvd_last_error", "pvd_good_fft_size", "pvd_good_fft_size_axis", "pvd_plan_create", "pvd_plan_create_ex", "pvd_plan_get_info",
     "pvd_plan_workspace_bytes", "pvd_plan_set_workspace", "pvd_plan_set_kernel", "pvd_conv_execute", "pvd_conv_execute_batch", "pvd_conv_forward_planes", "pvd_conv_finish", "pvd_conv_middle", "pvd_conv_output_planes", "pvd_plan_reserve_sms", "pvd_stream_write_flag", "pvd_stream_wait_flag_geq", "pvd_copy_async", "pvd_plan_destroy", "pvd_plan_set_profiling", "pvd_plan_get_pass_times", "pvd_plan_check_device_errors",
-    "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_monoexp_integral",
+    "pvd_kernel_eval_radial", "pvd_hu_to_density_f32", "pvd_hu_to_density_i16", "pvd_weighted_sum", "pvd_weighted_combine", "pvd_monoexp_integral",
     "pvd_density_scale", "pvd_monoexp_fit", "pvd_ct_prepare", "pvd_roi_minmax", "pvd_dvh_histogram",
     "pvd_stager_create", "pvd_stager_destroy", "pvd_stage_h2d", "pvd_stage_d2h", "pvd_i16_to_f32",
 ]
@@ -103,6 +103,7 @@ class PvdLib:
         d.pvd_hu_to_density_f32.argtypes = [vp, fp, C.c_int, vp, C.c_size_t, vp]
         d.pvd_hu_to_density_i16.argtypes = [vp, fp, C.c_int, vp, C.c_size_t, vp]
         d.pvd_weighted_sum.argtypes = [C.POINTER(vp), fp, C.c_int, vp, C.c_size_t, vp]
+        d.pvd_weighted_combine.argtypes = [C.POINTER(vp), C.c_int, fp, C.POINTER(vp), C.c_int, C.c_size_t, vp]
         d.pvd_monoexp_integral.argtypes = [vp, vp, C.c_float, vp, C.c_size_t, vp]
         d.pvd_density_scale.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, C.c_size_t, vp]
         d.pvd_monoexp_fit.argtypes = [C.POINTER(vp), fp, fp, C.c_int, C.c_float, C.c_float, vp, vp, vp, C.c_size_t, vp]
@@ -248,6 +249,16 @@ class PvdLib:
         ptrs = (C.c_void_p * T)(*vol_ptrs)
         w = (C.c_float * T)(*[float(x) for x in weights])
         self.check(self.dll.pvd_weighted_sum(ptrs, w, T, out_ptr, n, stream))
+
+    def weighted_combine(self, vol_ptrs: Sequence[int], W: Sequence[Sequence[float]], out_ptrs: Sequence[int], n: int, stream: int = 0):
+        """out[j] = sum_t W[j][t] * vol[t] in one pass (pvd_weighted_combine)."""
+        T, J = len(vol_ptrs), len(out_ptrs)
+        if len(W) != J or any(len(row) != T for row in W):
+            raise ValueError("W must have one row of T weights per output")
+        ptrs = (C.c_void_p * T)(*vol_ptrs)
+        outs = (C.c_void_p * J)(*out_ptrs)
+        w = (C.c_float * (J * T))(*[float(x) for row in W for x in row])
+        self.check(self.dll.pvd_weighted_combine(ptrs, T, w, outs, J, n, stream))
 
     def monoexp_integral(self, a0_ptr: int, lam_ptr: int, t_limit: float, out_ptr: int, n: int, stream: int = 0):
         self.check(self.dll.pvd_monoexp_integral(a0_ptr, lam_ptr, t_limit, out_ptr, n, stream))

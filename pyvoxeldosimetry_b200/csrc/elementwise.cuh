@@ -74,17 +74,80 @@ __global__ void rescale_to_f32_kernel(const T* __restrict__ in, float slope, flo
         out[i] = fmaf(slope, (float)in[i], intercept);
 }
 
-struct WsumArgs {
+// J weighted combinations of T volumes in one pass: out_j = sum_t w[j][t] * v_t.  Every input is read once and every output
+// written once: 4 (T + J) bytes per voxel.  This is ActivitySampler._trapezoid_integration (J = 1, core/activity_sampler.py:
+// 69-79), the trapezoid of precomputed dose rates, and interpolate_timepoints (core/utils.py:154-191) - scipy's interp1d of
+// kind linear / cubic / previous is a LINEAR map of the sampled volumes whose T x J weights depend on the time points only,
+// so the host computes the weights and the volumes make one trip through HBM.  A zero weight skips its product (an unused
+// volume may hold anything, as with interp1d), a NaN weight makes the output NaN ('previous' before the first time point).
+constexpr int kMaxJ = 16;
+struct WcombArgs {
     const float* v[kMaxT];
-    float w[kMaxT];
-    int T;
+    float* o[kMaxJ];
+    float w[kMaxJ][kMaxT];
+    unsigned used;  // bit t: some output has a non-zero weight on volume t (others are never loaded)
+    int T, J;
 };
 
-__global__ void weighted_sum_kernel(const WsumArgs a, float* __restrict__ out, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float acc = 0.f;
-        for (int t = 0; t < a.T; ++t) acc += a.w[t] * __ldg(a.v[t] + i);
-        out[i] = acc;
+template <int JJ>  // compile-time bound of the outputs (accumulators stay in registers); a.J <= JJ of them are stored
+__global__ void __launch_bounds__(256) weighted_combine_kernel(const WcombArgs a, size_t n, int vec) {
+    const size_t ngroups = (n + 3) / 4;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * blockDim.x) {
+        const size_t i0 = 4 * g;
+        const bool full = vec && i0 + 4 <= n;
+        float4 acc[JJ];
+        PVD_UNROLL
+        for (int j = 0; j < JJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // four volumes per trip: their loads are issued together (memory-level parallelism), then the products
+        for (int t0 = 0; t0 < a.T; t0 += 4) {
+            float4 x[4];
+            PVD_UNROLL
+            for (int q = 0; q < 4; ++q) {
+                const int t = t0 + q;
+                x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < a.T && ((a.used >> t) & 1u)) {
+                    const float* __restrict__ src = a.v[t] + i0;
+                    if (full) {
+                        x[q] = *reinterpret_cast<const float4*>(src);
+                    } else {
+                        x[q].x = src[0];
+                        if (i0 + 1 < n) x[q].y = src[1];
+                        if (i0 + 2 < n) x[q].z = src[2];
+                        if (i0 + 3 < n) x[q].w = src[3];
+                    }
+                }
+            }
+            PVD_UNROLL
+            for (int q = 0; q < 4; ++q) {
+                const int t = t0 + q;
+                if (t < a.T) {
+                    PVD_UNROLL
+                    for (int j = 0; j < JJ; ++j) {
+                        const float w = a.w[j][t];
+                        if (w != 0.f) {  // NaN != 0: a NaN weight propagates
+                            acc[j].x = fmaf(w, x[q].x, acc[j].x);
+                            acc[j].y = fmaf(w, x[q].y, acc[j].y);
+                            acc[j].z = fmaf(w, x[q].z, acc[j].z);
+                            acc[j].w = fmaf(w, x[q].w, acc[j].w);
+                        }
+                    }
+                }
+            }
+        }
+        PVD_UNROLL
+        for (int j = 0; j < JJ; ++j) {
+            if (j < a.J) {
+                float* __restrict__ dst = a.o[j] + i0;
+                if (full) {
+                    *reinterpret_cast<float4*>(dst) = acc[j];
+                } else {
+                    dst[0] = acc[j].x;
+                    if (i0 + 1 < n) dst[1] = acc[j].y;
+                    if (i0 + 2 < n) dst[2] = acc[j].z;
+                    if (i0 + 3 < n) dst[3] = acc[j].w;
+                }
+            }
+        }
     }
 }
 

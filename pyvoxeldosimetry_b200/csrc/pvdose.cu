@@ -191,10 +191,11 @@ struct FastRows {
             (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES + Sched<N, R1, R2, R3>::TOTAL * sizeof(float2) + 16, NT \
     }
 // separate radix schedules for the forward (NTF threads, F1 F2 F3) and the inverse (NTI threads, I1 I2 I3) direction
-#define PVD_ROWS2(N, NTF, F1, F2, F3, NTI, I1, I2, I3)                                                                   \
+#define PVD_ROWS2(N, NTF, F1, F2, F3, NTI, I1, I2, I3) PVD_ROWS2M(N, 1, NTF, F1, F2, F3, NTI, I1, I2, I3)
+#define PVD_ROWS2M(N, MINB, NTF, F1, F2, F3, NTI, I1, I2, I3)                                                            \
     {                                                                                                                    \
         N, NTF, rows_fwd_fast_kernel<N, NTF, F1, F2, F3>, rows_inv_fast_kernel<N, NTI, I1, I2, I3>,                      \
-            rows_fwd_pipe_kernel<N, NTF, 1, F1, F2, F3>, rows_inv_pipe_kernel<N, NTI, 1, I1, I2, I3>,                    \
+            rows_fwd_pipe_kernel<N, NTF, MINB, F1, F2, F3>, rows_inv_pipe_kernel<N, NTI, MINB, I1, I2, I3>,              \
             (size_t)N * 17 * sizeof(float2) + RowStage<N>::BYTES +                                                       \
                 (Sched<N, F1, F2, F3>::TOTAL > Sched<N, I1, I2, I3>::TOTAL ? Sched<N, F1, F2, F3>::TOTAL                 \
                                                                            : Sched<N, I1, I2, I3>::TOTAL) * sizeof(float2) + 16, \
@@ -225,8 +226,11 @@ const FastRows kFastRows[] = {
     PVD_ROWS(400, 320, 2, 20, 20, 1),
     PVD_ROWS(256, 256, 3, 16, 16, 1),
     PVD_ROWS(512, 512, 1, 8, 8, 8),
-    PVD_ROWS(432, 384, 1, 18, 24, 1),   // 400 + kernel reach
-    PVD_ROWS(288, 288, 2, 16, 18, 1),
+    // 400 / 256 + kernel reach ('same' mode).  Schedules per direction (profiles/r02_ab_rows_small.jsonl): the 432-point inverse
+    // with three stages and 576 threads 0.308 -> 0.285 ms (its forward pass is faster with two: 0.202 vs 0.211-0.221), the
+    // 288-point inverse as 18*16 0.041 -> 0.039 ms
+    PVD_ROWS2M(432, 1, 384, 18, 24, 1, 576, 6, 6, 12),
+    PVD_ROWS2M(288, 2, 288, 16, 18, 1, 288, 18, 16, 1),
     // The long rows leave room for ONE CTA per SM, so every block-wide barrier idles the SM: two big-radix stages (one
     // exchange per transform) beat three small ones wherever the registers hold (profiles/r02_ab_long_rows.jsonl: 800 forward
     // 1.74 -> 1.42 ms, 840 forward 2.54 -> 1.69 ms, 840 inverse 3.13 -> 2.39 ms per 1024^2 / 1152^2 rows; the 800-point inverse
@@ -1333,21 +1337,49 @@ int pvd_i16_to_f32(const void* d_in, int is_unsigned, float slope, float interce
     return PVD_OK;
 }
 
-int pvd_weighted_sum(const float* const* h_vol, const float* h_weights, int T, float* out, size_t n, void* stream) {
-    if (!h_vol || !out) return fail(PVD_ERR_INVALID, "null argument");
+int pvd_weighted_combine(const float* const* h_vol, int T, const float* h_W, float* const* h_out, int J, size_t n, void* stream) {
+    if (!h_vol || !h_out) return fail(PVD_ERR_INVALID, "null argument");
     if (T < 1 || T > PVD_MAX_T) return fail(PVD_ERR_INVALID, "T=%d outside [1,%d]", T, PVD_MAX_T);
-    WsumArgs a;
+    if (J < 1 || J > kMaxJ) return fail(PVD_ERR_INVALID, "J=%d outside [1,%d]", J, kMaxJ);
+    WcombArgs a;
     memset(&a, 0, sizeof a);
     a.T = T;
+    a.J = J;
+    bool vec = true;
     for (int t = 0; t < T; ++t) {
         if (!h_vol[t]) return fail(PVD_ERR_INVALID, "volume pointer %d is null", t);
         a.v[t] = h_vol[t];
-        a.w[t] = h_weights ? h_weights[t] : 1.f;
+        vec = vec && ((uintptr_t)h_vol[t] % 16 == 0);
+    }
+    for (int j = 0; j < J; ++j) {
+        if (!h_out[j]) return fail(PVD_ERR_INVALID, "output pointer %d is null", j);
+        a.o[j] = h_out[j];
+        vec = vec && ((uintptr_t)h_out[j] % 16 == 0);
+        for (int t = 0; t < T; ++t) {
+            const float w = h_W ? h_W[(size_t)j * T + t] : 1.f;
+            a.w[j][t] = w;
+            if (w != 0.f) a.used |= 1u << t;
+        }
     }
     if (n == 0) return PVD_OK;
-    PVD_LAUNCH(weighted_sum_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, a, out, n);
-    PVD_CUDA_CHECK("weighted_sum_kernel");
+    const size_t ngroups = (n + 3) / 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (J == 1)
+        PVD_LAUNCH(weighted_combine_kernel<1>, dim3(ew_grid(ngroups)), dim3(256), 0, st, a, n, (int)vec);
+    else if (J <= 4)
+        PVD_LAUNCH(weighted_combine_kernel<4>, dim3(ew_grid(ngroups)), dim3(256), 0, st, a, n, (int)vec);
+    else if (J <= 8)
+        PVD_LAUNCH(weighted_combine_kernel<8>, dim3(ew_grid(ngroups)), dim3(256), 0, st, a, n, (int)vec);
+    else
+        PVD_LAUNCH(weighted_combine_kernel<16>, dim3(ew_grid(ngroups)), dim3(256), 0, st, a, n, (int)vec);
+    PVD_CUDA_CHECK("weighted_combine_kernel");
     return PVD_OK;
+}
+
+int pvd_weighted_sum(const float* const* h_vol, const float* h_weights, int T, float* out, size_t n, void* stream) {
+    if (!out) return fail(PVD_ERR_INVALID, "null argument");
+    float* const outs[1] = {out};
+    return pvd_weighted_combine(h_vol, T, h_weights, outs, 1, n, stream);
 }
 
 int pvd_monoexp_integral(const float* A0, const float* lambda, float t_limit, float* out, size_t n, void* stream) {

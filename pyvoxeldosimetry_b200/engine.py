@@ -340,6 +340,38 @@ def weighted_sum(vols: Sequence[torch.Tensor], weights: Sequence[float]) -> torc
     return out
 
 
+MAX_J = 16
+
+
+def weighted_combine(vols: Sequence[torch.Tensor], W) -> list:
+    """[sum_t W[j][t] * vols[t] for j] with every volume read once per pass of <= MAX_J outputs (pvd_weighted_combine).
+    More than MAX_T volumes: the weights are applied chunk by chunk, later chunks accumulate onto the outputs in place."""
+    dev = require_cuda(vols[0].device)
+    W = [[float(x) for x in row] for row in W]
+    T = len(vols)
+    if any(len(row) != T for row in W):
+        raise ValueError("every weight row needs one entry per volume")
+    vols = [v if v.is_contiguous() else v.contiguous() for v in vols]
+    outs = [torch.empty_like(vols[0]) for _ in W]
+    lib = get_lib()
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(dev)
+        for j0 in range(0, len(W), MAX_J):
+            rows, oj = W[j0:j0 + MAX_J], outs[j0:j0 + MAX_J]
+            if T <= MAX_T:
+                lib.weighted_combine([v.data_ptr() for v in vols], rows, [o.data_ptr() for o in oj], vols[0].numel(), stream)
+                continue
+            # long series: each output is (previous partial sum) + the next MAX_T - 1 volumes; J partial sums ride along
+            # one at a time because a pass takes at most MAX_T inputs
+            for o, row in zip(oj, rows):
+                lib.weighted_combine([v.data_ptr() for v in vols[:MAX_T]], [row[:MAX_T]], [o.data_ptr()], o.numel(), stream)
+                for t0 in range(MAX_T, T, MAX_T - 1):
+                    chunk = vols[t0:t0 + MAX_T - 1]
+                    lib.weighted_combine([v.data_ptr() for v in chunk] + [o.data_ptr()], [row[t0:t0 + MAX_T - 1] + [1.0]],
+                                         [o.data_ptr()], o.numel(), stream)
+    return outs
+
+
 def monoexp_integral(A0: torch.Tensor, lam: torch.Tensor, t_limit: float) -> torch.Tensor:
     dev = require_cuda(A0.device)
     out = torch.empty_like(A0)

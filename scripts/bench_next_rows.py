@@ -51,5 +51,22 @@ ms2 = timeit(lambda: engine.dvh_histogram(dose, mask, edges), reps=10)
 nb = 5 * dose.numel()
 res['dvh_512x512x400_minmax'] = {'ms': ms1, 'algorithmic_bytes': nb, 'gbs': nb / ms1 / 1e6, 'frac_of_measured_peak': nb / ms1 / 1e6 / peak, 'note': 'includes the 16-byte D2H + stream sync'}
 res['dvh_512x512x400_histogram_1000bins'] = {'ms': ms2, 'algorithmic_bytes': nb, 'gbs': nb / ms2 / 1e6, 'frac_of_measured_peak': nb / ms2 / 1e6 / peak}
+del dose, mask, hu
+torch.cuda.empty_cache()
+# time-axis combinations (pvd_weighted_combine): the trapezoid sum of 4 volumes at the C3 size, and interpolate_timepoints
+# (4 sampled 256^3 volumes -> 8 interpolated ones; linear = 2 weights per output, cubic = dense weights)
+from pyvoxeldosimetry_b200.core.utils import interpolation_weights
+vols = [torch.rand(shape, device=dev, generator=g) for _ in range(4)]
+ms = timeit(lambda: engine.weighted_sum(vols, [0.5, 1.0, 1.0, 0.5]), reps=10)
+nb = 4 * 5 * vols[0].numel()
+res['weighted_sum_512x512x400_T4'] = {'ms': ms, 'algorithmic_bytes': nb, 'gbs': nb / ms / 1e6, 'frac_of_measured_peak': nb / ms / 1e6 / peak}
+del vols
+vols = [torch.rand((256, 256, 256), device=dev, generator=g) for _ in range(4)]
+times, new = [4.0, 24.0, 96.0, 168.0], list(np.linspace(4.0, 168.0, 8))
+for kind in ('linear', 'cubic'):
+    W = interpolation_weights(times, new, kind).tolist()
+    ms = timeit(lambda: engine.weighted_combine(vols, W), reps=20)
+    nb = 4 * (4 + 8) * vols[0].numel()
+    res[f'interpolate_timepoints_256^3_T4_to_8_{kind}'] = {'ms': ms, 'algorithmic_bytes': nb, 'gbs': nb / ms / 1e6, 'frac_of_measured_peak': nb / ms / 1e6 / peak}
 res['peak_gbs_measured'] = peak
 print(json.dumps(res))

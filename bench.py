@@ -568,10 +568,11 @@ def run_c5(args, dev, dist, rank, world, steps, boundary):
 
 
 def dram_traffic_for(build_id: str, workload: str, boundary: str):
-    """dram__bytes_read + write of the whole path from the committed ncu --set full capture - only when the capture was
-    taken from THIS build of the kernels (the file carries the library's build id)."""
-    p = os.path.join(REPO, "profiles", "r02_dram_traffic_c3.json")
-    if workload != "c3" or boundary != "reference" or not os.path.exists(p):
+    """dram__bytes_read + write of the whole path from the committed ncu capture of this workload - only when the capture was
+    taken from THIS build of the kernels (the file carries the library's build id).  c3 / reference: ncu --set full."""
+    name = "r02_dram_traffic_c3.json" if (workload, boundary) == ("c3", "reference") else f"r02_dram_traffic_{workload}_{boundary}.json"
+    p = os.path.join(REPO, "profiles", name)
+    if not os.path.exists(p):
         return None, "no capture for this workload"
     d = json.load(open(p))
     if d.get("build_id") != build_id:

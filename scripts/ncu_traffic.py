@@ -1,5 +1,5 @@
 """raw ncu csv (ncu -i X.ncu-rep --page raw --csv) -> per-kernel DRAM traffic JSON used by bench.py's roofline.traffic.
-usage: python scripts/ncu_traffic.py raw.csv out.json "<note>" """
+usage: python scripts/ncu_traffic.py raw.csv out.json "<note>" [library build id] """
 import csv, json, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, data = rows[0], rows[2:]
@@ -19,5 +19,7 @@ for r in data:
     total += rd + wr
 out['_whole_path_dram_bytes'] = total
 out['_note'] = sys.argv[3] if len(sys.argv) > 3 else ''
+if len(sys.argv) > 4:
+    out['build_id'] = sys.argv[4].strip()  # bench.py reports roofline.traffic only from a capture of the library it runs
 json.dump(out, open(sys.argv[2], 'w'), indent=1)
 print(json.dumps(out, indent=1))

@@ -29,5 +29,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:direct_conv_cubic -s 2 -c 1 -o $O/prof_direct python scripts/profile_c3.py same 4 512x512x400 5x5x5 > $O/ncu_direct.log 2>&1
 ncu -i $O/prof_direct.ncu-rep --page raw --csv > $O/prof_direct_raw.csv 2>/dev/null
 python -c "from pyvoxeldosimetry_b200._capi import get_lib; print(get_lib().build_id())" > $O/build_id.txt
-rm -f $O/prof_c3.ncu-rep.tmp
+# gpurun copies at most 64 MiB back: keep the full C3 report, drop the others once their raw pages are extracted
+rm -f $O/prof_c3.ncu-rep.tmp $O/prof_direct.ncu-rep $O/prof_c3same.ncu-rep $O/prof_c2.ncu-rep
+du -sh gpurun_out
 ls -la $O

@@ -271,6 +271,15 @@ def reference_step_real(calc, maps64, times, vox, rho):
     return d
 
 
+def arm_config(wl, boundary):
+    """The `config` object of the bench line - IDENTICAL for both arms (`--impl ours` / `--impl reference`) of one workload, so
+    that the driver can see that they measured the same thing; what differs between the arms goes into `impl_config`."""
+    nbytes = 4 * int(np.prod(wl["shape"])) * (wl["T"] + (1 if wl["density"] else 0))
+    return {"workload": wl["desc"], "boundary": boundary, "volumes_per_step_per_gpu": 1,
+            "l2": (f"inputs ({nbytes / 1e6:.0f} MB per step) exceed the 126 MB L2, nothing to flush" if nbytes > 126e6 else
+                   "small workload: inputs fit the 126 MB L2 (launch-bound), not flushed")}
+
+
 def run_reference(args, wl):
     """`--impl reference`: the UNMODIFIED reference class on the full workload shape, on this box's host cores
     (np.fft is single-threaded by construction: cores = 1).  Every step is one full volume: K steps + W warm-ups of
@@ -309,9 +318,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "boundary": args.boundary, "volumes_per_step_per_gpu": 1,
-                   "l2": "inputs (>=419 MB per volume for c3) exceed the 126 MB L2",
-                   "parallelism": "one host process, one thread (the reference has no parallelism)"},
+        "config": arm_config(wl, args.boundary),
+        "impl_config": {"parallelism": "one host process, one thread (the reference has no parallelism)"},
         "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count(), "finite": bool(np.isfinite(d).all())},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -700,10 +708,10 @@ def run_ours(args, wl):
             "metric": "dose_volumes_per_sec", "value": value, "unit": "volumes/s", "voxels_per_sec": value * nvox,
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "boundary": args.boundary, "fft_shape": list(info.m),
-                       "volumes_per_step_per_gpu": 1, "l2": f"inputs + work buffer ({info.workspace_bytes / 2e6:.0f} MB per pass) exceed the 126 MB L2"
-                       if info.workspace_bytes > 4e8 else "small workload: L2-resident (launch-bound), not flushed",
-                       "parallelism": f"independent volumes sharded over {world} rank(s), no data-path collective", "library_build_id": build_id},
+            "config": arm_config(wl, args.boundary),
+            "impl_config": {"fft_shape": list(info.m), "work_buffer_mb_per_pass": round(info.workspace_bytes / 2e6),
+                            "parallelism": f"independent volumes sharded over {world} rank(s), no data-path collective",
+                            "library_build_id": build_id},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
                          "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "traffic_source": traffic_src,
                          "what": "whole conv path (all launches of one volume): algorithmic 4*(T+1+[density]) B/voxel / time per volume",

@@ -351,6 +351,9 @@ def weighted_combine(vols: Sequence[torch.Tensor], W) -> list:
     T = len(vols)
     if any(len(row) != T for row in W):
         raise ValueError("every weight row needs one entry per volume")
+    for v in vols:
+        if v.dtype != torch.float32 or v.device != vols[0].device or v.shape != vols[0].shape:
+            raise ValueError("weighted_combine takes float32 CUDA tensors of one shape on one device")
     vols = [v if v.is_contiguous() else v.contiguous() for v in vols]
     outs = [torch.empty_like(vols[0]) for _ in W]
     lib = get_lib()

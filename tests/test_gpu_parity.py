@@ -226,6 +226,9 @@ def test_c3_full_size_vs_oracle(torch_cuda):
     ((270, 64, 100), "same", (320, None, None)),       # 256-plane slab + halo -> <320>
     ((150, 48, 60), "same", (180, None, None)),        # 128-plane slab + halo -> <180>
     ((165, 48, 60), "same", (192, None, None)),        # -> <192>
+    ((24, 40, 400), "same", (None, None, 432)),        # 400 + kernel reach -> rows <432>: forward 18*24, inverse 6*6*12 (576 threads)
+    ((24, 262, 262), "same", (None, 288, 288)),        # 256 + reach -> <288>: rows forward 16*18 / inverse 18*16, y passes <288>
+    ((270, 40, 262), "same", (320, None, 288)),        # x walk <320> over rows <288>
 ])
 def test_slab_menu_sizes_vs_oracle(torch_cuda, shape, boundary, fft_shape):
     from pyvoxeldosimetry_b200.engine import ConvPlan

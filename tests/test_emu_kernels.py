@@ -198,6 +198,10 @@ FAST_CASES = [
     ((3, 5, 800), (2, 2, 9), 0, 1, True),      # rows <800> 8*10*10, pipelined, one CTA per SM
     ((2, 6, 840), (1, 3, 25), 1, 1, True),     # rows <864> 8*9*12: same mode 840 -> 864, no staging pipeline
     ((3, 5, 816), (2, 2, 49), 1, 1, True),     # rows <840> 8*7*15: same mode 816 -> 840, the longest pipelined row length
+    ((3, 5, 416), (2, 2, 33), 1, 1, True),     # rows <432>: same mode 416 -> 432, forward 18*24 (384 threads), inverse 6*6*12 (576 threads)
+    ((3, 5, 276), (2, 2, 25), 1, 2, False),    # rows <288>: forward 16*18, inverse 18*16
+    ((320, 3, 4), (9, 2, 1), 0, 1, True),      # x <320> 16*20 as the one-tile-per-CTA walk (4-rank slab of the 1024-plane volume)
+    ((288, 3, 4), (9, 2, 1), 0, 1, False),     # x <288> 16*18, same walk
 ]
 
 
